@@ -1,0 +1,124 @@
+/*
+ * kmerpapa_b200.h — C ABI of libkpapa.so, the B200 (sm_100a) implementation of kmerPaPa's
+ * optimal k-mer pattern-partition dynamic program.
+ *
+ * The reference (BesenbacherLab/kmerPaPa v0.2.4) is pure Python + numba and has no FFI layer; its
+ * drop-in boundary is the pair of Python functions cli.py calls.  Each entry point below names
+ * the reference code it replaces (paths relative to the reference checkout):
+ *
+ *   kp_pack_counts     src/kmerpapa/io_utils.py:82-136 (read_dict dedup/sum) +
+ *                      src/kmerpapa/algorithms/bottum_up_array_w_numba.py:106-114 (level-0 fill)
+ *   kp_expand_counts   bottum_up_array_w_numba.py:50-53 and
+ *                      bottum_up_array_penalty_plus_pseudo_CV.py:52-59 (pattern counts = sum of two
+ *                      disjoint sub-patterns; train = total - held-out)
+ *   kp_dp_single       bottum_up_array_w_numba.py:26-64,116-120 (score + min-plus recurrence)
+ *   kp_backtrack       bottum_up_array_w_numba.py:8-24 (DFS, c1 subtree first)
+ *   kp_dp_cv_job       bottum_up_array_penalty_plus_pseudo_CV.py:15-78,145-157, one fold per call
+ *   kp_pattern_counts  src/kmerpapa/pattern_utils.py:192-215 (get_M_U, used by cli.py:281-283)
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; kp_last_error() gives the message
+ *     (thread-local).  No function falls back to a CPU path: without a usable CUDA device the
+ *     plan cannot be created and everything else fails.
+ *   - d_* are device pointers owned by the caller (the Python host allocates them as torch
+ *     tensors), h_* are host pointers.  `stream` is a cudaStream_t passed as void*.
+ *   - tables are stored tile-major: tile = dense_index / tile_cells, cell = dense_index % tile_cells,
+ *     element (tile, cell) at tile * tile_stride + cell (tile_stride >= tile_cells, padded to 32).
+ *     dense_index is the reference's pattern number (pattern_utils.py:237-257).
+ *   - a plan is bound to one device and one general pattern; it is not thread-safe, different
+ *     plans may be used from different threads.
+ */
+#ifndef KMERPAPA_B200_H
+#define KMERPAPA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kp_plan kp_plan;
+
+typedef struct kp_plan_info {
+    uint64_t npat;           /* number of patterns = prod radix_i (pattern_utils.py:587-599) */
+    uint64_t nkmer;          /* number of k-mers matched by the general pattern */
+    uint64_t ntiles;         /* npat / tile_cells */
+    uint64_t table_elems;    /* ntiles * tile_stride: elements of d_best / d_split / d_tt */
+    uint64_t expanded_elems; /* ntiles * tile_kmers: elements of each expanded count table */
+    uint64_t backtrack_ws_bytes; /* bytes of device workspace kp_backtrack needs for `cap` = 65536 */
+    uint32_t k;              /* pattern length */
+    uint32_t nlevels;        /* pattern_level(gen_pat) + 1 */
+    uint32_t tile_cells;     /* patterns per tile (product of the radices of the low positions) */
+    uint32_t tile_stride;    /* padded tile pitch in elements */
+    uint32_t tile_kmers;     /* k-mers spanned by the low positions */
+    uint32_t low_positions;  /* number of (non-fixed) positions kept on chip */
+    uint32_t high_levels;    /* number of tile waves = launches of the DP kernel */
+    uint32_t sm_count;
+} kp_plan_info;
+
+const char *kp_last_error(void);
+int kp_version(void);
+
+/* gen_pat: IUPAC general pattern, e.g. "NNNNANNNN".  device: CUDA ordinal. */
+int kp_plan_create(const char *gen_pat, int device, kp_plan **out);
+int kp_plan_destroy(kp_plan *plan);
+int kp_plan_get_info(const kp_plan *plan, kp_plan_info *out);
+
+/*
+ * K1.  h_codes[n]: one k-mer per entry, 4 bits per position (one-hot A=1,C=2,G=4,T=8), position 0 in
+ * the least significant nibble; h_pos/h_neg: its positive and negative counts.  Entries naming the
+ * same k-mer are summed.  d_kmerM/d_kmerU: int64[nkmer] in k-mer index order (position 0 fastest,
+ * bases in the reference's `code` order).  k <= 16.
+ */
+int kp_pack_counts(kp_plan *plan, const uint64_t *h_codes, const int64_t *h_pos, const int64_t *h_neg, uint64_t n,
+                   int64_t *d_kmerM, int64_t *d_kmerU, void *stream);
+
+/* K2.  d_exp*: int64[expanded_elems]; counts of every (high-digit tile) x (low k-mer). */
+int kp_expand_counts(kp_plan *plan, const int64_t *d_kmerM, const int64_t *d_kmerU, int64_t *d_expM,
+                     int64_t *d_expU, void *stream);
+
+/*
+ * K3+K4.  Full DP.  d_best: float32[table_elems] best loss per pattern; d_split: uint8[table_elems],
+ * position*8 + split_index of the winning two-way split, 0xFF when the pattern is kept whole.
+ * max_count: upper bound of any pattern count (n_mut + n_unmut); selects 32- or 64-bit on-chip counts.
+ */
+int kp_dp_single(kp_plan *plan, const int64_t *d_expM, const int64_t *d_expU, uint64_t max_count, double alpha,
+                 double beta, double penalty, float *d_best, uint8_t *d_split, void *stream);
+
+/*
+ * K5.  Partition of the general pattern, dense pattern numbers in the reference's emission order.
+ * d_ws: device workspace of kp_backtrack_ws_bytes(cap).  Synchronises `stream`.
+ */
+uint64_t kp_backtrack_ws_bytes(uint64_t cap);
+int kp_backtrack(kp_plan *plan, const uint8_t *d_split, void *d_ws, uint64_t cap, uint64_t *h_patnums,
+                 uint64_t *n_out, void *stream);
+
+/*
+ * One cross-validation job = one fold x alpha x penalty.  d_exp?tot: all-fold totals, d_exp?test: the
+ * fold's held-out counts (both from kp_expand_counts); train counts are formed on device as
+ * total - held-out.  d_tt: float32[2 * table_elems], (train, test) interleaved per pattern.
+ * h_top[2]: train and held-out loss of the general pattern (written after synchronising `stream`);
+ * may be NULL to leave the result on the device and not synchronise.
+ */
+int kp_dp_cv_job(kp_plan *plan, const int64_t *d_expMtot, const int64_t *d_expUtot, const int64_t *d_expMtest,
+                 const int64_t *d_expUtest, uint64_t max_count, double alpha, double beta_fold, double penalty,
+                 float *d_tt, float *h_top, void *stream);
+
+/* Counts of arbitrary patterns (dense numbers) straight from the k-mer tables.  Synchronises. */
+int kp_pattern_counts(kp_plan *plan, const int64_t *d_kmerM, const int64_t *d_kmerU, const uint64_t *h_patnums,
+                      uint64_t n, int64_t *h_M, int64_t *h_U, void *stream);
+
+/* Number of kernel launches issued through this plan so far (for bench.py's gpu_launches). */
+uint64_t kp_plan_launch_count(const kp_plan *plan);
+
+/* Test hook: y[i] = device log(x[i]) (the glibc-exact restatement used by the scoring kernels). */
+int kp_debug_log(int device, const double *h_x, double *h_y, uint64_t n);
+/* Test hook: level-0 score of (M,U) pairs on the device (scipy xlogy/xlog1py restated). */
+int kp_debug_leaf_score(int device, const int64_t *h_M, const int64_t *h_U, uint64_t n, double alpha, double beta,
+                        double penalty, double *h_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMERPAPA_B200_H */

@@ -1,0 +1,51 @@
+"""Fold sampling for cross validation, on the host.
+
+Bit parity with the reference needs the exact stream of numpy's legacy RandomState, so this stays
+numpy on the CPU (reference: src/kmerpapa/CV_tools.py:5-62).  The sampler deals every count of
+every k-mer into nfolds held-out folds: k-mers sorted as strings, urn colours = all positive counts
+followed by all negative counts, nfolds-1 sequential multivariate-hypergeometric draws of
+total//nfolds balls each, the last fold takes what is left.
+"""
+import numpy as np
+
+
+def draw_multivariate_hypergeometric(m, colors, prng):
+    """One draw of m balls without replacement from an urn with colors[i] balls of colour i, as a
+    chain of univariate hypergeometric draws (same call sequence as the reference's `sample`)."""
+    ncol = len(colors)
+    tail = np.cumsum(colors[::-1])[::-1]  # tail[i] = balls of colour >= i
+    picked = np.zeros(ncol, dtype=colors.dtype)
+    for i in range(ncol - 1):
+        if m < 1:
+            break
+        picked[i] = prng.hypergeometric(colors[i], tail[i + 1], m)
+        m -= picked[i]
+    picked[-1] = m
+    return picked
+
+
+def sample_fold_counts(kmers, pos, neg, nfolds, prng, itype=np.uint64):
+    """Held-out counts per fold.
+
+    kmers: list of k-mer strings; pos/neg: their counts (same order).
+    Returns (Mf, Uf), arrays [len(kmers), nfolds] in the order of `kmers`.
+    """
+    n = len(kmers)
+    order = sorted(range(n), key=kmers.__getitem__)
+    urn = np.empty(2 * n, dtype=itype)
+    for r, i in enumerate(order):
+        urn[r] = pos[i]
+        urn[n + r] = neg[i]
+    per_fold = urn.sum() // nfolds
+    draws = np.empty((2 * n, nfolds), dtype=itype)
+    for f in range(nfolds - 1):
+        got = draw_multivariate_hypergeometric(per_fold, urn, prng)
+        draws[:, f] = got
+        urn -= got
+    draws[:, nfolds - 1] = urn
+    Mf = np.empty((n, nfolds), dtype=itype)
+    Uf = np.empty((n, nfolds), dtype=itype)
+    inv = np.asarray(order)
+    Mf[inv] = draws[:n]
+    Uf[inv] = draws[n:]
+    return Mf, Uf

@@ -1,0 +1,66 @@
+"""ctypes binding of libkpapa.so (C ABI in include/kmerpapa_b200.h)."""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libkpapa.so")
+_lib = None
+
+
+class KpError(RuntimeError):
+    pass
+
+
+class PlanInfo(ctypes.Structure):
+    _fields_ = [
+        ("npat", ctypes.c_uint64), ("nkmer", ctypes.c_uint64), ("ntiles", ctypes.c_uint64),
+        ("table_elems", ctypes.c_uint64), ("expanded_elems", ctypes.c_uint64),
+        ("backtrack_ws_bytes", ctypes.c_uint64),
+        ("k", ctypes.c_uint32), ("nlevels", ctypes.c_uint32), ("tile_cells", ctypes.c_uint32),
+        ("tile_stride", ctypes.c_uint32), ("tile_kmers", ctypes.c_uint32), ("low_positions", ctypes.c_uint32),
+        ("high_levels", ctypes.c_uint32), ("sm_count", ctypes.c_uint32),
+    ]
+
+
+# every symbol include/kmerpapa_b200.h declares: name -> (restype, argtypes)
+_vp, _u64, _i64, _dbl, _int, _cp = (ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64, ctypes.c_double, ctypes.c_int,
+                                   ctypes.c_char_p)
+SYMBOLS = {
+    "kp_last_error": (_cp, []),
+    "kp_version": (_int, []),
+    "kp_plan_create": (_int, [_cp, _int, ctypes.POINTER(_vp)]),
+    "kp_plan_destroy": (_int, [_vp]),
+    "kp_plan_get_info": (_int, [_vp, ctypes.POINTER(PlanInfo)]),
+    "kp_pack_counts": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp]),
+    "kp_expand_counts": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "kp_dp_single": (_int, [_vp, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
+    "kp_backtrack_ws_bytes": (_u64, [_u64]),
+    "kp_backtrack": (_int, [_vp, _vp, _vp, _u64, _vp, ctypes.POINTER(_u64), _vp]),
+    "kp_dp_cv_job": (_int, [_vp, _vp, _vp, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
+    "kp_pattern_counts": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp]),
+    "kp_plan_launch_count": (_u64, [_vp]),
+    "kp_debug_log": (_int, [_int, _vp, _vp, _u64]),
+    "kp_debug_leaf_score": (_int, [_int, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp]),
+}
+
+
+def lib():
+    """Load libkpapa.so.  Fails loudly when it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise KpError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(kmerpapa_b200 has no CPU implementation of the DP)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().kp_last_error()
+        raise KpError(f"{what}: {msg.decode() if msg else 'error ' + str(rc)}")

@@ -1,0 +1,198 @@
+"""Cross-validation grid over (pseudo-count alpha, penalty): one GPU DP per fold x alpha x penalty.
+
+Drop-in for the reference's src/kmerpapa/algorithms/bottum_up_array_penalty_plus_pseudo_CV.py
+(`pattern_partition_bottom_up`, :81-177; called from cli.py:232): same name, arguments, return
+values, CVfile rows and stderr lines.
+
+What changed underneath: the reference carries all folds on the last axis of one numba DP; folds never
+interact inside that DP (_CV.py:46-51, :63-78), so here a job is one (iteration, fold, alpha, penalty)
+and runs as an independent single-fold DP on the GPU (kp_dp_cv_job), with train counts formed on the
+device as total - held-out.  Jobs are dealt to the ranks of torch.distributed (one process per GPU)
+in contiguous fold-major chunks and the per-job (train, held-out) losses of the general pattern are
+all-gathered (NCCL on GPUs); every rank then does the reference's float32 fold sum and selection.
+"""
+import sys
+
+import numpy as np
+
+from .. import CV_tools, iupac
+from ..score_utils import get_betas
+from .bottum_up_array_w_numba import count_dtype, kmer_arrays
+
+
+# ---------------------------------------------------------------------------------------------
+# job sharding (pure host logic; exercised on CPU with gloo in tests/)
+# ---------------------------------------------------------------------------------------------
+def job_list(nit, nfolds, n_alpha, n_penalty):
+    """All jobs, fold-major so that a contiguous chunk touches as few folds as possible."""
+    return [(it, f, a_i, p_i) for it in range(nit) for f in range(nfolds) for a_i in range(n_alpha)
+            for p_i in range(n_penalty)]
+
+
+def shard_bounds(njobs, rank, world):
+    """Contiguous chunk [lo, hi) of rank; chunks differ by at most one job."""
+    base, extra = divmod(njobs, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def dist_info():
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
+def gather_job_results(local, njobs, rank, world, device=None):
+    """local: float32 [hi-lo, 2] results of this rank's chunk -> float32 [njobs, 2] on every rank.
+    One all_gather of equally padded chunks (NCCL when the tensors live on a GPU, gloo on CPU)."""
+    if world == 1:
+        return local
+    import torch
+    import torch.distributed as dist
+
+    chunk = -(-njobs // world)
+    pad = np.zeros((chunk, 2), dtype=np.float32)
+    pad[: local.shape[0]] = local
+    t = torch.from_numpy(pad)
+    if device is not None:
+        t = t.to(device)
+    out = torch.empty((world * chunk, 2), dtype=torch.float32, device=t.device)
+    dist.all_gather_into_tensor(out, t)
+    out = out.cpu().numpy().reshape(world, chunk, 2)
+    full = np.empty((njobs, 2), dtype=np.float32)
+    for r in range(world):
+        lo, hi = shard_bounds(njobs, r, world)
+        full[lo:hi] = out[r, : hi - lo]
+    return full
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side reduction and selection (reference :165-177)
+# ---------------------------------------------------------------------------------------------
+def fold_sum(values, nit):
+    """Python sum() over np.float32 values then / nit: sequential float32 accumulation."""
+    return sum(list(values)) / nit
+
+
+def select_best(alphas, penalties, results, nit, nfolds, k, cvfile=None):
+    """results: float32 [nit, nfolds, n_alpha, n_penalty, 2].  Writes one CVfile row per grid point and
+    returns (alpha, penalty, test) of the first strict minimum, alpha outer / penalty inner."""
+    best_test_loss = 1e100
+    best_values = (None, None)
+    for a_i, alpha in enumerate(alphas):
+        for p_i, penalty in enumerate(penalties):
+            vals = [results[it, f, a_i, p_i, 1] for it in range(nit) for f in range(nfolds)]
+            test = fold_sum(vals, nit)
+            if cvfile is not None:
+                print(k, alpha, penalty, test, file=cvfile)
+            if test < best_test_loss:
+                best_values = (alpha, penalty)
+                best_test_loss = test
+    return best_values[0], best_values[1], best_test_loss
+
+
+def covering_patterns_per_kmer(gen_pat):
+    """Number of sub-patterns of gen_pat that contain a given k-mer (8 per N, 4 per 3-letter, 2 per 2-letter)."""
+    c = 1
+    for ch in gen_pat:
+        c *= 1 << (len(iupac.CODE[ch]) - 1)
+    return c
+
+
+class GpuFoldRunner:
+    """Runs single-fold DP jobs of one CV iteration on this process's GPU."""
+
+    def __init__(self, gen_pat, codes, pos, neg, device=None):
+        from ..engine import get_plan
+
+        self.plan = get_plan(gen_pat, device)
+        self.codes = codes
+        self.max_count = int(pos.sum()) + int(neg.sum())
+        kM, kU = self.plan.pack_counts(codes, pos, neg, name="cvtot_k")
+        self.tot = self.plan.expand(kM, kU, name="cvtot_e")
+        self.folds = {}
+
+    def set_folds(self, Mf, Uf):
+        self.Mf, self.Uf = Mf, Uf
+        self.folds = {}
+
+    def _fold(self, f):
+        if f not in self.folds:
+            kM, kU = self.plan.pack_counts(self.codes, self.Mf[:, f], self.Uf[:, f], name="cvfold_k")
+            self.folds[f] = self.plan.expand(kM, kU, name=f"cvfold{f}_e")
+        return self.folds[f]
+
+    def run(self, f, alpha, beta, penalty):
+        eMte, eUte = self._fold(f)
+        return self.plan.cv_job(self.tot[0], self.tot[1], eMte, eUte, self.max_count, alpha, beta, penalty)
+
+    @property
+    def device(self):
+        return self.plan.device
+
+
+def run_grid(gen_pat, kmers, codes, pos, neg, alphas, penalties, nfolds, nit, seed, verbosity=0, runner=None,
+             gather_device="auto"):
+    """Core of the CV: returns float32 results [nit, nfolds, n_alpha, n_penalty, 2] (train, held-out)."""
+    rank, world = dist_info()
+    prng = np.random.RandomState(seed)
+    if runner is None:
+        runner = GpuFoldRunner(gen_pat, codes, pos, neg)
+    if gather_device == "auto":
+        gather_device = getattr(runner, "device", None)
+    na, npen = len(alphas), len(penalties)
+    jobs = job_list(nit, nfolds, na, npen)
+    lo, hi = shard_bounds(len(jobs), rank, world)
+    local = np.zeros((hi - lo, 2), dtype=np.float32)
+    cover = covering_patterns_per_kmer(gen_pat)
+    prev_M = prev_U = None
+    for it in range(nit):
+        if verbosity > 0 and nit > 1:
+            print("CV Iteration", it, file=sys.stderr)
+        Mf, Uf = CV_tools.sample_fold_counts(kmers, pos, neg, nfolds, prng)
+        if verbosity > 0:
+            print("CV sampling DONE", file=sys.stderr)
+        # per-fold held-out totals.  The reference sums ALL rows of its np.empty tables (_CV.py:134-135):
+        # zero pages on the first iteration, the previous iteration's upper-level rows afterwards.
+        M_sum_test = Mf.sum(axis=0)
+        U_sum_test = Uf.sum(axis=0)
+        if prev_M is not None:
+            M_sum_test = M_sum_test + np.uint64(cover - 1) * prev_M
+            U_sum_test = U_sum_test + np.uint64(cover - 1) * prev_U
+        prev_M, prev_U = Mf.sum(axis=0), Uf.sum(axis=0)
+        M_sum_train = M_sum_test.sum() - M_sum_test
+        U_sum_train = U_sum_test.sum() - U_sum_test
+        betas = [get_betas(alpha, M_sum_train, U_sum_train) for alpha in alphas]
+        runner.set_folds(Mf, Uf)
+        for j in range(max(lo, it * nfolds * na * npen), min(hi, (it + 1) * nfolds * na * npen)):
+            _, f, a_i, p_i = jobs[j]
+            tr, te = runner.run(f, alphas[a_i], betas[a_i][f], penalties[p_i])
+            local[j - lo, 0], local[j - lo, 1] = tr, te
+    full = gather_job_results(local, len(jobs), rank, world, gather_device)
+    return full.reshape(nit, nfolds, na, npen, 2)
+
+
+def pattern_partition_bottom_up(gen_pat, contextD, alphas, args, nmut, nunmut, penalties, index_mut=0):
+    """Returns (best_alpha, best_penalty, np.float32 best_test_loss); writes the CVfile rows
+    `k alpha penalty test` and the reference's progress lines on stderr."""
+    nf, nit = args.nfolds, args.iterations
+    kmers = list(contextD.keys())
+    codes, pos, neg = kmer_arrays(contextD, index_mut)
+    verbosity = getattr(args, "verbosity", 0)
+    results = run_grid(gen_pat, kmers, codes, pos, neg, alphas, penalties, nf, nit, args.seed, verbosity)
+    rank, _ = dist_info()
+    if verbosity > 0 and rank == 0:
+        for it in range(nit):
+            for a_i, alpha in enumerate(alphas):
+                for p_i, penalty in enumerate(penalties):
+                    row = results[it, :, a_i, p_i, 1]
+                    print(f"CV on k={len(gen_pat)} alpha={alpha} penalty={penalty} i={it} test_LL={sum(row)}", file=sys.stderr)
+                    if verbosity > 1:
+                        print(f"test LL for each fold: {row}", file=sys.stderr)
+    cvfile = args.CVfile if rank == 0 else None
+    return select_best(alphas, penalties, results, nit, nf, len(gen_pat), cvfile)

@@ -1,0 +1,63 @@
+"""Optimal pattern partition of one data set: the single DP + backtrack, on the GPU.
+
+Drop-in for the reference's src/kmerpapa/algorithms/bottum_up_array_w_numba.py
+(`pattern_partition_bottom_up`, :67-124; called from cli.py:279): same name, arguments, return types
+and partition order.  The numba array DP is replaced by the CUDA path behind libkpapa.so:
+pack k-mer counts (K1) -> expand counts (K2) -> wave-front DP with fused FP64 scoring (K3+K4) ->
+device backtrack (K5).
+"""
+import sys
+
+import numpy as np
+
+from .. import iupac
+from ..engine import get_plan
+
+
+def kmer_arrays(contextD, index_mut=0):
+    """contextD {kmer: (n_pos, ..., n_neg)} -> packed codes and int64 count columns."""
+    n = len(contextD)
+    codes = np.empty(n, dtype=np.uint64)
+    pos = np.empty(n, dtype=np.int64)
+    neg = np.empty(n, dtype=np.int64)
+    for r, (kmer, tup) in enumerate(contextD.items()):
+        codes[r] = iupac.kmer_code(kmer)
+        pos[r] = tup[index_mut]
+        neg[r] = tup[-1]
+    return codes, pos, neg
+
+
+def count_dtype(nmut, nunmut):
+    """The reference keeps counts as uint32 unless the totals need 64 bits (w_numba.py:82-85)."""
+    return np.uint64 if nmut + nunmut > np.iinfo(np.uint32).max else np.uint32
+
+
+def partition_from_arrays(gen_pat, codes, pos, neg, alpha, beta, penalty, device=None, want_counts=False):
+    """Array-level entry (host buffers in, host results out): returns (np.float32 loss,
+    dense pattern numbers of the partition in emission order[, (M, U) per pattern])."""
+    plan = get_plan(gen_pat, device)
+    kM, kU = plan.pack_counts(codes, pos, neg)
+    eM, eU = plan.expand(kM, kU)
+    max_count = int(pos.sum()) + int(neg.sum())
+    best, split = plan.dp_single(eM, eU, max_count, alpha, beta, penalty)
+    patnums = plan.backtrack(split)
+    loss = plan.top_score(best)
+    if want_counts:
+        return loss, patnums, plan.pattern_counts(kM, kU, patnums)
+    return loss, patnums
+
+
+def pattern_partition_bottom_up(gen_pat, contextD, alpha_, beta_, penalty_, args, nmut, nunmut, index_mut=0):
+    """Returns (np.float32 loss, M, U, names): loss of the optimal partition of gen_pat, total positive
+    and negative counts (numpy unsigned scalars like the reference's M_mem/U_mem entries), and the
+    partition's patterns in the reference's backtrack order (c1 subtree first)."""
+    gen_pat_level = iupac.pattern_level(gen_pat)
+    if getattr(args, "verbosity", 0) > 1:
+        for level in range(1, gen_pat_level + 1):
+            print(f"level {level} of {gen_pat_level}", file=sys.stderr)
+    codes, pos, neg = kmer_arrays(contextD, index_mut)
+    loss, patnums = partition_from_arrays(gen_pat, codes, pos, neg, alpha_, beta_, penalty_)
+    PE = iupac.PatternEnumeration(gen_pat)
+    names = [PE.num2pattern(p) for p in patnums]
+    itype = count_dtype(nmut, nunmut)
+    return loss, itype(pos.sum()), itype(neg.sum()), names

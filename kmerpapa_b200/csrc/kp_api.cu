@@ -1,0 +1,359 @@
+// kp_api.cu — C ABI of libkpapa.so (see include/kmerpapa_b200.h for the contract).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/kmerpapa_b200.h"
+#include "kp_kernels.cuh"
+#include "kp_plan.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string &msg)
+{
+    g_err = msg;
+    return 1;
+}
+
+#define KP_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                        std::to_string(__LINE__) + ")");                                      \
+    } while (0)
+
+}  // namespace
+
+struct kp_plan {
+    KpHostPlan host;
+    int device = 0;
+    int sm_count = 0;
+    KpTables *d_tab = nullptr;
+    uint32_t *d_cells = nullptr;
+    uint32_t *d_tiles = nullptr;
+    uint8_t *d_genmask = nullptr;
+    int *d_err = nullptr;
+    uint64_t launches = 0;
+    int occ[2][2] = {{0, 0}, {0, 0}};  // resident CTAs per SM of the DP kernel [cv][wide]
+    size_t smem[2][2] = {{0, 0}, {0, 0}};
+};
+
+extern "C" {
+
+const char *kp_last_error(void) { return g_err.c_str(); }
+int kp_version(void) { return 100; }
+
+static const void *dp_kernel_ptr(bool cv, bool wide)
+{
+    if (!cv) return wide ? (const void *)kp_dp_wave_kernel<false, true> : (const void *)kp_dp_wave_kernel<false, false>;
+    return wide ? (const void *)kp_dp_wave_kernel<true, true> : (const void *)kp_dp_wave_kernel<true, false>;
+}
+
+int kp_plan_create(const char *gen_pat, int device, kp_plan **out)
+{
+    if (!gen_pat || !out) return fail("kp_plan_create: null argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(std::string("kp_plan_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU path");
+    if (device < 0 || device >= ndev) return fail("kp_plan_create: bad device ordinal");
+    KP_CUDA(cudaSetDevice(device));
+    kp_plan *p = new kp_plan();
+    std::string err;
+    if (kp_build_host_plan(gen_pat, p->host, err)) { delete p; return fail("kp_plan_create: " + err); }
+    p->device = device;
+    cudaDeviceProp prop;
+    KP_CUDA(cudaGetDeviceProperties(&prop, device));
+    p->sm_count = prop.multiProcessorCount;
+    const KpTables &t = p->host.t;
+    KP_CUDA(cudaMalloc(&p->d_tab, sizeof(KpTables)));
+    KP_CUDA(cudaMemcpy(p->d_tab, &t, sizeof(KpTables), cudaMemcpyHostToDevice));
+    KP_CUDA(cudaMalloc(&p->d_cells, sizeof(uint32_t) * p->host.cell_list.size()));
+    KP_CUDA(cudaMemcpy(p->d_cells, p->host.cell_list.data(), sizeof(uint32_t) * p->host.cell_list.size(), cudaMemcpyHostToDevice));
+    KP_CUDA(cudaMalloc(&p->d_tiles, sizeof(uint32_t) * p->host.tile_order.size()));
+    KP_CUDA(cudaMemcpy(p->d_tiles, p->host.tile_order.data(), sizeof(uint32_t) * p->host.tile_order.size(), cudaMemcpyHostToDevice));
+    KP_CUDA(cudaMalloc(&p->d_genmask, KP_MAXK));
+    KP_CUDA(cudaMemcpy(p->d_genmask, p->host.gen_mask, KP_MAXK, cudaMemcpyHostToDevice));
+    KP_CUDA(cudaMalloc(&p->d_err, sizeof(int)));
+    KP_CUDA(cudaMemset(p->d_err, 0, sizeof(int)));
+    for (int cv = 0; cv < 2; cv++)
+        for (int wide = 0; wide < 2; wide++) {
+            size_t sm = kp_dp_smem_bytes(cv, wide, t.tile_cells, t.tile_stride, t.nlow);
+            p->smem[cv][wide] = sm;
+            if (sm > (size_t)prop.sharedMemPerBlockOptin) { p->occ[cv][wide] = 0; continue; }
+            const void *fn = dp_kernel_ptr(cv, wide);
+            // the attribute is per function, not per plan: always raise it to the device maximum
+            KP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+            int nb = 0;
+            KP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, KP_NT, sm));
+            p->occ[cv][wide] = nb;
+        }
+    *out = p;
+    return 0;
+}
+
+int kp_plan_destroy(kp_plan *p)
+{
+    if (!p) return 0;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_tab);
+    cudaFree(p->d_cells);
+    cudaFree(p->d_tiles);
+    cudaFree(p->d_genmask);
+    cudaFree(p->d_err);
+    delete p;
+    return 0;
+}
+
+uint64_t kp_backtrack_ws_bytes(uint64_t cap) { return (3 * cap) * sizeof(KpBtNode) + cap * 8 + 64; }
+
+int kp_plan_get_info(const kp_plan *p, kp_plan_info *o)
+{
+    if (!p || !o) return fail("kp_plan_get_info: null argument");
+    const KpTables &t = p->host.t;
+    memset(o, 0, sizeof *o);
+    o->npat = p->host.npat;
+    o->nkmer = p->host.nkmer;
+    o->ntiles = t.ntiles;
+    o->table_elems = (uint64_t)t.ntiles * t.tile_stride;
+    o->expanded_elems = (uint64_t)t.ntiles * t.tile_kmers;
+    o->backtrack_ws_bytes = kp_backtrack_ws_bytes(65536);
+    o->k = (uint32_t)p->host.k;
+    o->nlevels = t.total_level + 1;
+    o->tile_cells = t.tile_cells;
+    o->tile_stride = t.tile_stride;
+    o->tile_kmers = t.tile_kmers;
+    o->low_positions = (uint32_t)t.nlow;
+    o->high_levels = (uint32_t)(p->host.hl_off.size() - 1);
+    o->sm_count = (uint32_t)p->sm_count;
+    return 0;
+}
+
+uint64_t kp_plan_launch_count(const kp_plan *p) { return p ? p->launches : 0; }
+
+static int grid_for(uint64_t n, int threads, int sm_count)
+{
+    uint64_t b = (n + threads - 1) / threads;
+    uint64_t cap = (uint64_t)sm_count * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+int kp_pack_counts(kp_plan *p, const uint64_t *h_codes, const int64_t *h_pos, const int64_t *h_neg, uint64_t n,
+                   int64_t *d_kmerM, int64_t *d_kmerU, void *stream)
+{
+    if (!p) return fail("kp_pack_counts: null plan");
+    if (p->host.k > 16) return fail("kp_pack_counts: packed codes hold at most 16 positions");
+    cudaStream_t st = (cudaStream_t)stream;
+    KP_CUDA(cudaSetDevice(p->device));
+    KP_CUDA(cudaMemsetAsync(d_kmerM, 0, p->host.nkmer * 8, st));
+    KP_CUDA(cudaMemsetAsync(d_kmerU, 0, p->host.nkmer * 8, st));
+    if (n == 0) return 0;
+    unsigned long long *d_codes = nullptr;
+    long long *d_pos = nullptr, *d_neg = nullptr;
+    KP_CUDA(cudaMallocAsync(&d_codes, n * 8, st));
+    KP_CUDA(cudaMallocAsync(&d_pos, n * 8, st));
+    KP_CUDA(cudaMallocAsync(&d_neg, n * 8, st));
+    KP_CUDA(cudaMemcpyAsync(d_codes, h_codes, n * 8, cudaMemcpyHostToDevice, st));
+    KP_CUDA(cudaMemcpyAsync(d_pos, h_pos, n * 8, cudaMemcpyHostToDevice, st));
+    KP_CUDA(cudaMemcpyAsync(d_neg, h_neg, n * 8, cudaMemcpyHostToDevice, st));
+    KP_CUDA(cudaMemsetAsync(p->d_err, 0, sizeof(int), st));
+    kp_pack_kernel<<<grid_for(n, 256, p->sm_count), 256, 0, st>>>(p->d_tab, p->d_genmask, p->host.k, d_codes, d_pos, d_neg, n,
+                                                                  (long long *)d_kmerM, (long long *)d_kmerU, p->d_err);
+    p->launches++;
+    KP_CUDA(cudaGetLastError());
+    int herr = 0;
+    KP_CUDA(cudaMemcpyAsync(&herr, p->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaFreeAsync(d_codes, st));
+    KP_CUDA(cudaFreeAsync(d_pos, st));
+    KP_CUDA(cudaFreeAsync(d_neg, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    if (herr) return fail("kp_pack_counts: a k-mer code is not one-hot or lies outside the general pattern");
+    return 0;
+}
+
+int kp_expand_counts(kp_plan *p, const int64_t *d_kmerM, const int64_t *d_kmerU, int64_t *d_expM, int64_t *d_expU,
+                     void *stream)
+{
+    if (!p) return fail("kp_expand_counts: null plan");
+    cudaStream_t st = (cudaStream_t)stream;
+    KP_CUDA(cudaSetDevice(p->device));
+    const KpTables &t = p->host.t;
+    kp_expand_base_kernel<<<grid_for(p->host.nkmer, 256, p->sm_count), 256, 0, st>>>(
+        p->d_tab, p->host.nkmer, (const long long *)d_kmerM, (const long long *)d_kmerU, (long long *)d_expM, (long long *)d_expU);
+    p->launches++;
+    uint64_t total = (uint64_t)t.ntiles * t.tile_kmers;
+    for (int e = t.nlow; e < t.npos; e++) {
+        kp_expand_pass_kernel<<<grid_for(total, 256, p->sm_count), 256, 0, st>>>(p->d_tab, e, (long long *)d_expM, (long long *)d_expU);
+        p->launches++;
+    }
+    KP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int launch_dp(kp_plan *p, bool cv, bool wide, KpDpParams prm, cudaStream_t st)
+{
+    int occ = p->occ[cv][wide];
+    if (occ < 1) return fail("DP kernel does not fit in shared memory for this tile shape");
+    size_t smem = p->smem[cv][wide];
+    size_t nhl = p->host.hl_off.size() - 1;
+    for (size_t l = 0; l < nhl; l++) {
+        uint64_t lo = p->host.hl_off[l], hi = p->host.hl_off[l + 1];
+        if (hi == lo) continue;
+        prm.tile_list = p->d_tiles + lo;
+        prm.ntiles_wave = (uint32_t)(hi - lo);
+        prm.leaf_wave = (l == 0);
+        uint64_t grid = hi - lo;
+        uint64_t cap = (uint64_t)p->sm_count * occ;
+        if (grid > cap) grid = cap;
+        if (!cv) {
+            if (wide) kp_dp_wave_kernel<false, true><<<(int)grid, KP_NT, smem, st>>>(prm);
+            else kp_dp_wave_kernel<false, false><<<(int)grid, KP_NT, smem, st>>>(prm);
+        } else {
+            if (wide) kp_dp_wave_kernel<true, true><<<(int)grid, KP_NT, smem, st>>>(prm);
+            else kp_dp_wave_kernel<true, false><<<(int)grid, KP_NT, smem, st>>>(prm);
+        }
+        p->launches++;
+    }
+    KP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int kp_dp_single(kp_plan *p, const int64_t *d_expM, const int64_t *d_expU, uint64_t max_count, double alpha, double beta,
+                 double penalty, float *d_best, uint8_t *d_split, void *stream)
+{
+    if (!p) return fail("kp_dp_single: null plan");
+    KP_CUDA(cudaSetDevice(p->device));
+    KpDpParams prm;
+    memset(&prm, 0, sizeof prm);
+    prm.tab = p->d_tab;
+    prm.cell_list = p->d_cells;
+    prm.e0 = (const long long *)d_expM;
+    prm.e1 = (const long long *)d_expU;
+    prm.alpha = alpha; prm.beta = beta; prm.penalty = penalty;
+    prm.best = d_best;
+    prm.split = d_split;
+    bool wide = max_count > 0xFFFFFFFFull;
+    return launch_dp(p, false, wide, prm, (cudaStream_t)stream);
+}
+
+int kp_dp_cv_job(kp_plan *p, const int64_t *d_expMtot, const int64_t *d_expUtot, const int64_t *d_expMtest,
+                 const int64_t *d_expUtest, uint64_t max_count, double alpha, double beta_fold, double penalty, float *d_tt,
+                 float *h_top, void *stream)
+{
+    if (!p) return fail("kp_dp_cv_job: null plan");
+    KP_CUDA(cudaSetDevice(p->device));
+    KpDpParams prm;
+    memset(&prm, 0, sizeof prm);
+    prm.tab = p->d_tab;
+    prm.cell_list = p->d_cells;
+    prm.e0 = (const long long *)d_expMtot;
+    prm.e1 = (const long long *)d_expUtot;
+    prm.e2 = (const long long *)d_expMtest;
+    prm.e3 = (const long long *)d_expUtest;
+    prm.alpha = alpha; prm.beta = beta_fold; prm.penalty = penalty;
+    prm.tt = d_tt;
+    bool wide = max_count > 0xFFFFFFFFull;
+    if (launch_dp(p, true, wide, prm, (cudaStream_t)stream)) return 1;
+    if (h_top) {
+        const KpTables &t = p->host.t;
+        size_t top = ((size_t)(t.ntiles - 1) * t.tile_stride + (t.tile_cells - 1)) * 2;
+        KP_CUDA(cudaMemcpyAsync(h_top, d_tt + top, 2 * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        KP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    }
+    return 0;
+}
+
+int kp_backtrack(kp_plan *p, const uint8_t *d_split, void *d_ws, uint64_t cap, uint64_t *h_patnums, uint64_t *n_out,
+                 void *stream)
+{
+    if (!p || !d_ws || !h_patnums || !n_out) return fail("kp_backtrack: null argument");
+    if (p->host.t.total_level > 64) return fail("kp_backtrack: more than 64 levels");
+    cudaStream_t st = (cudaStream_t)stream;
+    KP_CUDA(cudaSetDevice(p->device));
+    KpBtNode *fa = (KpBtNode *)d_ws, *fb = fa + cap, *leaves = fb + cap;
+    unsigned long long *sorted = (unsigned long long *)(leaves + cap);
+    unsigned long long *counts = sorted + cap;
+    kp_backtrack_kernel<<<1, 256, 0, st>>>(p->d_tab, d_split, p->host.npat - 1, fa, fb, leaves, cap, counts);
+    p->launches++;
+    KP_CUDA(cudaGetLastError());
+    unsigned long long hc[2] = {0, 0};
+    KP_CUDA(cudaMemcpyAsync(hc, counts, sizeof hc, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    *n_out = hc[0];
+    if (hc[1] || hc[0] > cap) return fail("kp_backtrack: partition larger than the workspace capacity");
+    kp_backtrack_sort_kernel<<<(int)((hc[0] + 255) / 256), 256, 0, st>>>(leaves, counts, cap, sorted);
+    p->launches++;
+    KP_CUDA(cudaGetLastError());
+    KP_CUDA(cudaMemcpyAsync(h_patnums, sorted, hc[0] * 8, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int kp_pattern_counts(kp_plan *p, const int64_t *d_kmerM, const int64_t *d_kmerU, const uint64_t *h_patnums, uint64_t n,
+                      int64_t *h_M, int64_t *h_U, void *stream)
+{
+    if (!p) return fail("kp_pattern_counts: null plan");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    KP_CUDA(cudaSetDevice(p->device));
+    unsigned long long *d_pat = nullptr;
+    long long *d_out = nullptr;
+    KP_CUDA(cudaMallocAsync(&d_pat, n * 8, st));
+    KP_CUDA(cudaMallocAsync(&d_out, n * 16, st));
+    KP_CUDA(cudaMemcpyAsync(d_pat, h_patnums, n * 8, cudaMemcpyHostToDevice, st));
+    kp_pattern_counts_kernel<<<(int)n, 256, 0, st>>>(p->d_tab, p->host.nkmer, (const long long *)d_kmerM,
+                                                     (const long long *)d_kmerU, d_pat, d_out, d_out + n);
+    p->launches++;
+    KP_CUDA(cudaGetLastError());
+    KP_CUDA(cudaMemcpyAsync(h_M, d_out, n * 8, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaMemcpyAsync(h_U, d_out + n, n * 8, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaFreeAsync(d_pat, st));
+    KP_CUDA(cudaFreeAsync(d_out, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int kp_debug_log(int device, const double *h_x, double *h_y, uint64_t n)
+{
+    KP_CUDA(cudaSetDevice(device));
+    double *dx = nullptr, *dy = nullptr;
+    KP_CUDA(cudaMalloc(&dx, n * 8));
+    KP_CUDA(cudaMalloc(&dy, n * 8));
+    KP_CUDA(cudaMemcpy(dx, h_x, n * 8, cudaMemcpyHostToDevice));
+    kp_debug_log_kernel<<<296, 256>>>(dx, dy, n);
+    KP_CUDA(cudaGetLastError());
+    KP_CUDA(cudaMemcpy(h_y, dy, n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(dx);
+    cudaFree(dy);
+    return 0;
+}
+
+int kp_debug_leaf_score(int device, const int64_t *h_M, const int64_t *h_U, uint64_t n, double alpha, double beta,
+                        double penalty, double *h_out)
+{
+    KP_CUDA(cudaSetDevice(device));
+    long long *dm = nullptr, *du = nullptr;
+    double *dout = nullptr;
+    KP_CUDA(cudaMalloc(&dm, n * 8));
+    KP_CUDA(cudaMalloc(&du, n * 8));
+    KP_CUDA(cudaMalloc(&dout, n * 8));
+    KP_CUDA(cudaMemcpy(dm, h_M, n * 8, cudaMemcpyHostToDevice));
+    KP_CUDA(cudaMemcpy(du, h_U, n * 8, cudaMemcpyHostToDevice));
+    kp_debug_leaf_kernel<<<296, 256>>>(dm, du, n, alpha, beta, penalty, dout);
+    KP_CUDA(cudaGetLastError());
+    KP_CUDA(cudaMemcpy(h_out, dout, n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(dm);
+    cudaFree(du);
+    cudaFree(dout);
+    return 0;
+}
+
+}  // extern "C"

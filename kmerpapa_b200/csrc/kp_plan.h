@@ -1,0 +1,26 @@
+// kp_plan.h — host-side construction of the per-general-pattern tables (no CUDA in here).
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "kp_tables.h"
+
+struct KpHostPlan {
+    std::string gen;
+    int k = 0;
+    uint64_t npat = 0, nkmer = 0;
+    KpTables t;                        // uploaded verbatim
+    std::vector<uint32_t> cell_list;   // per cell, sorted by mini-level: (cell << 16) | packed digits
+    std::vector<uint32_t> tile_order;  // tile ids sorted by (high level, tile id)
+    std::vector<uint64_t> hl_off;      // offsets of the high levels in tile_order (size nhl + 1)
+    uint8_t gen_mask[KP_MAXK];         // nucleotide subset of every string position (fixed ones too)
+    uint8_t eff_of_pos[KP_MAXK];       // string position -> effective position index, 0xFF if fixed
+};
+
+// Returns 0 on success; on failure fills err.
+int kp_build_host_plan(const char *gen_pat, KpHostPlan &P, std::string &err);
+
+// dense pattern number -> IUPAC string / nucleotide masks (host utility, mirrors num2pattern)
+void kp_num2masks(const KpHostPlan &P, uint64_t num, uint8_t *masks_out);

@@ -1,0 +1,184 @@
+"""Host-side driver of the CUDA pattern-partition engine.
+
+PyTorch is used for device memory and streams only; every computation goes through the C ABI of
+libkpapa.so (include/kmerpapa_b200.h).  One PartitionPlan per (general pattern, device).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _native
+from ._native import KpError, check
+
+_PLANS = {}
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise KpError("no CUDA device visible: kmerpapa_b200 runs the DP on the GPU only (no CPU fallback)")
+    return torch
+
+
+class PartitionPlan:
+    """Tables, launch geometry and reusable device buffers for one general pattern on one GPU."""
+
+    def __init__(self, gen_pat, device=None):
+        torch = _torch()
+        self.lib = _native.lib()
+        self.gen_pat = gen_pat
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        h = ctypes.c_void_p()
+        check(self.lib.kp_plan_create(gen_pat.encode(), self.device_index, ctypes.byref(h)), "kp_plan_create")
+        self.handle = h
+        info = _native.PlanInfo()
+        check(self.lib.kp_plan_get_info(h, ctypes.byref(info)), "kp_plan_get_info")
+        self.info = info
+        self.npat, self.nkmer = int(info.npat), int(info.nkmer)
+        self._buf = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.kp_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _stream(self):
+        torch = _torch()
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _buffer(self, name, n, dtype):
+        """Reusable device buffer (torch tensor) of at least n elements."""
+        torch = _torch()
+        t = self._buf.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(int(n), dtype=dtype, device=self.device)
+            self._buf[name] = t
+        return t
+
+    def release_buffers(self):
+        self._buf.clear()
+
+    @property
+    def launches(self):
+        return int(self.lib.kp_plan_launch_count(self.handle))
+
+    # -- K1: k-mer tables ------------------------------------------------------------------------
+    def pack_counts(self, codes, pos, neg, name="kmer"):
+        """Scatter (code, positive, negative) triples into dense int64 k-mer tables on the device."""
+        torch = _torch()
+        codes = np.ascontiguousarray(codes, dtype=np.uint64)
+        pos = np.ascontiguousarray(pos, dtype=np.int64)
+        neg = np.ascontiguousarray(neg, dtype=np.int64)
+        if not (codes.shape == pos.shape == neg.shape):
+            raise ValueError("codes/pos/neg must have the same length")
+        kM = self._buffer(name + "M", self.nkmer, torch.int64)
+        kU = self._buffer(name + "U", self.nkmer, torch.int64)
+        check(self.lib.kp_pack_counts(self.handle, codes.ctypes.data, pos.ctypes.data, neg.ctypes.data, codes.size,
+                                      kM.data_ptr(), kU.data_ptr(), self._stream()), "kp_pack_counts")
+        return kM, kU
+
+    def upload_kmer_tables(self, kmerM, kmerU, name="kmer"):
+        """Dense k-mer tables already in k-mer index order (used for the per-fold held-out counts)."""
+        torch = _torch()
+        kM = self._buffer(name + "M", self.nkmer, torch.int64)
+        kU = self._buffer(name + "U", self.nkmer, torch.int64)
+        hm = torch.from_numpy(np.ascontiguousarray(kmerM, dtype=np.int64))
+        hu = torch.from_numpy(np.ascontiguousarray(kmerU, dtype=np.int64))
+        kM[: self.nkmer].copy_(hm, non_blocking=False)
+        kU[: self.nkmer].copy_(hu, non_blocking=False)
+        return kM, kU
+
+    # -- K2: expanded counts ---------------------------------------------------------------------
+    def expand(self, kM, kU, name="exp"):
+        torch = _torch()
+        n = int(self.info.expanded_elems)
+        eM = self._buffer(name + "M", n, torch.int64)
+        eU = self._buffer(name + "U", n, torch.int64)
+        check(self.lib.kp_expand_counts(self.handle, kM.data_ptr(), kU.data_ptr(), eM.data_ptr(), eU.data_ptr(),
+                                        self._stream()), "kp_expand_counts")
+        return eM, eU
+
+    # -- K3+K4: single DP ------------------------------------------------------------------------
+    def dp_single(self, eM, eU, max_count, alpha, beta, penalty):
+        torch = _torch()
+        n = int(self.info.table_elems)
+        best = self._buffer("best", n, torch.float32)
+        split = self._buffer("split", n, torch.uint8)
+        check(self.lib.kp_dp_single(self.handle, eM.data_ptr(), eU.data_ptr(), int(max_count), float(alpha), float(beta),
+                                    float(penalty), best.data_ptr(), split.data_ptr(), self._stream()), "kp_dp_single")
+        return best, split
+
+    def top_score(self, best):
+        """np.float32 loss of the general pattern (device -> host read of one element)."""
+        idx = (int(self.info.ntiles) - 1) * int(self.info.tile_stride) + int(self.info.tile_cells) - 1
+        return np.float32(best[idx].item())
+
+    # -- K5: backtrack ---------------------------------------------------------------------------
+    def backtrack(self, split, cap=65536):
+        torch = _torch()
+        while True:
+            ws = self._buffer("btws", int(self.lib.kp_backtrack_ws_bytes(cap)), torch.uint8)
+            out = np.empty(cap, dtype=np.uint64)
+            n = ctypes.c_uint64(0)
+            rc = self.lib.kp_backtrack(self.handle, split.data_ptr(), ws.data_ptr(), cap, out.ctypes.data, ctypes.byref(n),
+                                       self._stream())
+            if rc == 0:
+                return out[: n.value].copy()
+            msg = self.lib.kp_last_error().decode()
+            if "capacity" in msg and cap < (1 << 26):
+                cap *= 8
+                continue
+            raise KpError("kp_backtrack: " + msg)
+
+    # -- CV job ----------------------------------------------------------------------------------
+    def cv_job(self, eMtot, eUtot, eMte, eUte, max_count, alpha, beta, penalty, read_top=True):
+        """One fold x alpha x penalty.  Returns (np.float32 train, np.float32 test) of the general pattern."""
+        torch = _torch()
+        n = int(self.info.table_elems)
+        tt = self._buffer("tt", 2 * n, torch.float32)
+        top = (ctypes.c_float * 2)()
+        check(self.lib.kp_dp_cv_job(self.handle, eMtot.data_ptr(), eUtot.data_ptr(), eMte.data_ptr(), eUte.data_ptr(),
+                                    int(max_count), float(alpha), float(beta), float(penalty), tt.data_ptr(),
+                                    ctypes.cast(top, ctypes.c_void_p) if read_top else None, self._stream()),
+              "kp_dp_cv_job")
+        if not read_top:
+            return tt
+        return np.float32(top[0]), np.float32(top[1])
+
+    # -- output stage ----------------------------------------------------------------------------
+    def pattern_counts(self, kM, kU, patnums):
+        patnums = np.ascontiguousarray(patnums, dtype=np.uint64)
+        M = np.empty(patnums.size, dtype=np.int64)
+        U = np.empty(patnums.size, dtype=np.int64)
+        check(self.lib.kp_pattern_counts(self.handle, kM.data_ptr(), kU.data_ptr(), patnums.ctypes.data, patnums.size,
+                                         M.ctypes.data, U.ctypes.data, self._stream()), "kp_pattern_counts")
+        return M, U
+
+    # -- test/debug views ------------------------------------------------------------------------
+    def unpad(self, table, width=1):
+        """Tile-padded device table -> dense host array in the reference's pattern numbering."""
+        nt, st, tc = int(self.info.ntiles), int(self.info.tile_stride), int(self.info.tile_cells)
+        v = table[: nt * st * width].view(nt, st, width)[:, :tc, :]
+        return v.reshape(nt * tc, width).cpu().numpy()
+
+
+def get_plan(gen_pat, device=None):
+    """Cached PartitionPlan per (general pattern, device)."""
+    torch = _torch()
+    dev = torch.cuda.current_device() if device is None else int(device)
+    key = (gen_pat, dev)
+    plan = _PLANS.get(key)
+    if plan is None:
+        plan = PartitionPlan(gen_pat, dev)
+        _PLANS[key] = plan
+    return plan
+
+
+def clear_plans():
+    _PLANS.clear()

@@ -1,0 +1,213 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the reference's golden tables and the
+CPU oracle.  Bit-exact everywhere: float32 score tables, split decisions, partitions, counts, CV losses.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_files
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint32 if a.dtype == np.float32 else np.uint64)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from kmerpapa_b200 import engine
+
+    return engine
+
+
+def _codes(gen_pat):
+    from kmerpapa_b200 import iupac
+
+    return np.array([iupac.kmer_code(k) for k in iupac.matches(gen_pat)], dtype=np.uint64)
+
+
+def _run_single(eng, gen_pat, M, U, alpha, beta, penalty, max_count=None):
+    plan = eng.get_plan(gen_pat)
+    kM, kU = plan.pack_counts(_codes(gen_pat), M, U)
+    eM, eU = plan.expand(kM, kU)
+    mc = int(np.sum(M, dtype=np.uint64) + np.sum(U, dtype=np.uint64)) if max_count is None else max_count
+    best, split = plan.dp_single(eM, eU, mc, alpha, beta, penalty)
+    return plan, plan.unpad(best)[:, 0], plan.unpad(split)[:, 0], plan.backtrack(split)
+
+
+def test_device_log_is_glibc_log(eng, oracle):
+    from kmerpapa_b200 import _native
+
+    rng = np.random.default_rng(5)
+    n = 1_000_000
+    xs = np.concatenate([
+        rng.random(n), 1.0 - rng.random(n) * 0.07, 1.0 + (rng.random(n) - 0.5) * 0.2,
+        np.exp(rng.uniform(-700, 700, n)), rng.random(n) * 1e-300,
+        np.abs(rng.integers(0, 2**63 - 1, n, dtype=np.int64).view(np.float64)),
+        np.array([0.0, 1.0, np.inf, 5e-324, 2.2250738585072014e-308, 0.9375, 1.064697265625, -1.0, np.nan]),
+    ])
+    xs = np.ascontiguousarray(xs)
+    y = np.empty_like(xs)
+    _native.check(_native.lib().kp_debug_log(0, xs.ctypes.data, y.ctypes.data, xs.size), "kp_debug_log")
+    ref = np.empty_like(xs)
+    oracle.lib().kpo_log_array(xs.ctypes.data, ref.ctypes.data, xs.size)
+    nan = np.isnan(ref)
+    assert np.array_equal(np.isnan(y), nan)
+    assert np.array_equal(_bits(y[~nan]), _bits(ref[~nan]))
+
+
+def test_device_leaf_score_is_scipy(eng):
+    import scipy.special as sp
+
+    from kmerpapa_b200 import _native
+
+    rng = np.random.default_rng(6)
+    n = 300_000
+    U = rng.integers(0, 5_000_000, n)
+    M = rng.binomial(U, rng.random(n) * 0.6)
+    M[:1000] = 0
+    U[500:1500] = 0
+    alpha, beta, pen = 0.8, 1234.5, 5.0
+    out = np.empty(n, dtype=np.float64)
+    M64, U64 = M.astype(np.int64), U.astype(np.int64)
+    _native.check(_native.lib().kp_debug_leaf_score(0, M64.ctypes.data, U64.ctypes.data, n, alpha, beta, pen,
+                                                    out.ctypes.data), "kp_debug_leaf_score")
+    p = (M64 + alpha) / (M64 + U64 + alpha + beta)
+    ref = -2 * (sp.xlogy(M64, p) + sp.xlog1py(U64, -p)) + pen
+    assert np.array_equal(_bits(out), _bits(ref))
+
+
+@pytest.mark.parametrize("path", golden_files("single"), ids=lambda p: p.split("single_")[-1][:-4])
+def test_single_dp_against_reference_tables(eng, oracle, path):
+    g = np.load(path)
+    gp = str(g["gen_pat"])
+    plan, best, split, patnums = _run_single(eng, gp, g["kmerM"], g["kmerU"], float(g["alpha"]), float(g["beta"]),
+                                             float(g["penalty"]))
+    assert np.array_equal(_bits(best), _bits(g["score"]))
+    kept = g["bt"] == np.arange(len(g["bt"]), dtype=np.uint64)
+    assert np.array_equal(split == 0xFF, kept)
+    from kmerpapa_b200 import iupac
+
+    PE = iupac.PatternEnumeration(gp)
+    assert [PE.num2pattern(p) for p in patnums] == [str(x) for x in g["names"]]
+    # split codes decode to the reference's c1 pointer
+    ref = oracle.single_dp(gp, g["kmerM"], g["kmerU"], float(g["alpha"]), float(g["beta"]), float(g["penalty"]))
+    assert np.array_equal(split, ref["split"])
+    # counts of the partition's patterns straight from the device k-mer tables
+    M, U = plan.pattern_counts(plan._buf["kmerM"], plan._buf["kmerU"], patnums)
+    assert np.array_equal(M.astype(np.uint64), g["M"][patnums.astype(np.int64)])
+    assert np.array_equal(U.astype(np.uint64), g["U"][patnums.astype(np.int64)])
+
+
+@pytest.mark.parametrize("path", golden_files("single"), ids=lambda p: p.split("single_")[-1][:-4])
+def test_single_dp_wide_counts_path(eng, path):
+    """Same data through the 64-bit on-chip count path (selected by max_count)."""
+    g = np.load(path)
+    gp = str(g["gen_pat"])
+    _, best, split, _ = _run_single(eng, gp, g["kmerM"], g["kmerU"], float(g["alpha"]), float(g["beta"]),
+                                    float(g["penalty"]), max_count=1 << 40)
+    assert np.array_equal(_bits(best), _bits(g["score"]))
+
+
+@pytest.mark.parametrize("path", golden_files("cv"), ids=lambda p: p.split("cv_")[-1][:-4])
+def test_cv_jobs_against_reference_tables(eng, oracle, path):
+    g = np.load(path)
+    gp, nf = str(g["gen_pat"]), int(g["nfolds"])
+    pn = oracle.kmer_patnums(gp).astype(np.int64)
+    Mf, Uf = g["M_folds"][pn], g["U_folds"][pn]            # held-out counts per k-mer and fold
+    Mtot, Utot = Mf.sum(axis=1), Uf.sum(axis=1)
+    Ms, Us = Mf.sum(axis=0), Uf.sum(axis=0)
+    Mtr, Utr = Ms.sum() - Ms, Us.sum() - Us
+    alphas, pens = [float(a) for a in g["alphas"]], [float(c) for c in g["penalties"]]
+    plan = eng.get_plan(gp)
+    kM, kU = plan.upload_kmer_tables(Mtot, Utot, name="t_tot")
+    tot = plan.expand(kM, kU, name="t_tot_e")
+    mc = int(Mtot.sum() + Utot.sum())
+    gi = 0
+    for a_i, alpha in enumerate(alphas):
+        my = Mtr / (Mtr + Utr)
+        betas = (alpha * (1.0 - my)) / my
+        for p_i, pen in enumerate(pens):
+            for f in range(nf):
+                kMf, kUf = plan.upload_kmer_tables(Mf[:, f], Uf[:, f], name="t_fold")
+                fold = plan.expand(kMf, kUf, name="t_fold_e")
+                for wide_mc in (mc, 1 << 40):
+                    tt = plan.cv_job(tot[0], tot[1], fold[0], fold[1], wide_mc, alpha, betas[f], pen, read_top=False)
+                    tab = plan.unpad(tt, width=2)
+                    assert np.array_equal(_bits(tab[:, 0]), _bits(g["train_tables"][gi][:, f]))
+                    if gi == len(alphas) * len(pens) - 1:
+                        assert np.array_equal(_bits(tab[:, 1]), _bits(g["last_test_table"][:, f]))
+                    else:
+                        _, te = oracle.cv_job(gp, Mtot, Utot, Mf[:, f], Uf[:, f], alpha, betas[f], pen)
+                        assert np.array_equal(_bits(tab[:, 1]), _bits(te))
+            gi += 1
+
+
+@pytest.mark.parametrize("gen_pat,seed", [("NNNNN", 1), ("NNNMNN", 2), ("RYNNANNKM", 3), ("VNNNH", 4), ("NNNNNN", 5),
+                                          ("SWNNBNA", 6), ("MMMMMMMMMM", 7)])
+def test_random_against_oracle(eng, oracle, gen_pat, seed):
+    """Larger general patterns (several tile waves, mixed radices) against the CPU oracle."""
+    rng = np.random.default_rng(seed)
+    _, nk, _ = oracle.plan_info(gen_pat)
+    U = (1 + rng.negative_binomial(2, 2 / (2 + 800.0), size=nk)) * (rng.random(nk) < 0.9)
+    M = rng.binomial(U, np.minimum(0.5, 0.02 * np.exp(rng.normal(0, 0.8, size=nk))))
+    alpha, pen = 1.0, 4.0
+    mu = M.sum() / (M.sum() + U.sum())
+    beta = alpha * (1 - mu) / mu
+    _, best, split, patnums = _run_single(eng, gen_pat, M, U, alpha, beta, pen)
+    ref = oracle.single_dp(gen_pat, M, U, alpha, beta, pen)
+    assert np.array_equal(_bits(best), _bits(ref["score"]))
+    assert np.array_equal(split, ref["split"])
+    assert np.array_equal(patnums, oracle.backtrack(gen_pat, ref["split"]))
+
+
+def test_7mer_test_data_final_dp(eng, oracle):
+    """BASELINE config 2's final DP (test_data 7-mers, alpha=10, penalty=6): 34 171 875 patterns."""
+    from kmerpapa_b200 import iupac
+
+    gp = "NNNMNNN"
+    kmers = iupac.matches(gp)
+    pos, bg = {}, {}
+    for line in open(f"{GOLDEN}/data/mutated_7mers.txt"):
+        k, c = line.split()
+        pos[k] = int(c)
+    for line in open(f"{GOLDEN}/data/background_7mers.txt"):
+        k, c = line.split()
+        bg[k] = int(c)
+    M = np.array([pos.get(k, 0) for k in kmers], dtype=np.int64)
+    U = np.array([bg.get(k, 0) for k in kmers], dtype=np.int64) - M
+    alpha = 10.0
+    mu = int(M.sum()) / (int(M.sum()) + int(U.sum()))
+    beta = (alpha * (1.0 - mu)) / mu
+    _, best, split, patnums = _run_single(eng, gp, M, U, alpha, beta, 6.0)
+    ref = oracle.single_dp(gp, M, U, alpha, beta, 6.0)
+    assert np.array_equal(_bits(best), _bits(ref["score"]))
+    assert np.array_equal(split, ref["split"])
+    PE = iupac.PatternEnumeration(gp)
+    names = [PE.num2pattern(p) for p in patnums]
+    assert len(names) == 270 and names[0] == "RCAATNT"       # recorded from the reference CLI
+    assert float(best[-1]) == 1324533.625
+
+
+def test_pack_counts_sums_duplicates_and_rejects_bad_codes(eng):
+    from kmerpapa_b200 import iupac
+    from kmerpapa_b200._native import KpError
+
+    gp = "NAN"
+    plan = eng.get_plan(gp)
+    kmers = iupac.matches(gp)
+    codes = np.array([iupac.kmer_code(k) for k in kmers] + [iupac.kmer_code("CAG")], dtype=np.uint64)
+    pos = np.arange(len(codes), dtype=np.int64)
+    neg = 10 * np.arange(len(codes), dtype=np.int64)
+    kM, kU = plan.pack_counts(codes, pos, neg)
+    hM = kM[: plan.nkmer].cpu().numpy()
+    idx = kmers.index("CAG")
+    assert hM[idx] == idx + len(kmers)
+    with pytest.raises(KpError):
+        plan.pack_counts(np.array([iupac.kmer_code("CCG")], dtype=np.uint64), np.ones(1, np.int64), np.ones(1, np.int64))
