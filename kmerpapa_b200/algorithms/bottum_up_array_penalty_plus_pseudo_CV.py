@@ -137,8 +137,9 @@ class GpuFoldRunner:
 
 
 def run_grid(gen_pat, kmers, codes, pos, neg, alphas, penalties, nfolds, nit, seed, verbosity=0, runner=None,
-             gather_device="auto"):
-    """Core of the CV: returns float32 results [nit, nfolds, n_alpha, n_penalty, 2] (train, held-out)."""
+             gather_device="auto", presampled=None):
+    """Core of the CV: returns float32 results [nit, nfolds, n_alpha, n_penalty, 2] (train, held-out).
+    presampled: optional list (one per iteration) of (Mf, Uf) held-out tables to use instead of sampling."""
     rank, world = dist_info()
     prng = np.random.RandomState(seed)
     if runner is None:
@@ -154,7 +155,10 @@ def run_grid(gen_pat, kmers, codes, pos, neg, alphas, penalties, nfolds, nit, se
     for it in range(nit):
         if verbosity > 0 and nit > 1:
             print("CV Iteration", it, file=sys.stderr)
-        Mf, Uf = CV_tools.sample_fold_counts(kmers, pos, neg, nfolds, prng)
+        if presampled is not None:
+            Mf, Uf = presampled[it]
+        else:
+            Mf, Uf = CV_tools.sample_fold_counts(kmers, pos, neg, nfolds, prng)
         if verbosity > 0:
             print("CV sampling DONE", file=sys.stderr)
         # per-fold held-out totals.  The reference sums ALL rows of its np.empty tables (_CV.py:134-135):
