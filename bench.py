@@ -208,10 +208,10 @@ def bench_single(args, rank, world, local):
         eM, eU = plan.expand(kM, kU)
         if ev:
             ev[0].record()
-        best, split = plan.dp_single(eM, eU, max_count, ALPHA, beta, PENALTY)
+        best, kept = plan.dp_single(eM, eU, max_count, ALPHA, beta, PENALTY)
         if ev:
             ev[1].record()
-        patnums = plan.backtrack(split)
+        patnums = plan.backtrack(best, kept)
         return plan.top_score(best), patnums
 
     for _ in range(args.warmup):

@@ -13,6 +13,7 @@
  *                      disjoint sub-patterns; train = total - held-out)
  *   kp_dp_single       bottum_up_array_w_numba.py:26-64,116-120 (score + min-plus recurrence)
  *   kp_backtrack       bottum_up_array_w_numba.py:8-24 (DFS, c1 subtree first)
+ *   kp_split_codes     the backtrack_mem entry of bottum_up_array_w_numba.py:48-49, :64
  *   kp_dp_cv_job       bottum_up_array_penalty_plus_pseudo_CV.py:15-78,145-157, one fold per call
  *   kp_pattern_counts  src/kmerpapa/pattern_utils.py:192-215 (get_M_U, used by cli.py:281-283)
  *
@@ -22,9 +23,10 @@
  *     plan cannot be created and everything else fails.
  *   - d_* are device pointers owned by the caller (the Python host allocates them as torch
  *     tensors), h_* are host pointers.  `stream` is a cudaStream_t passed as void*.
- *   - tables are stored tile-major: tile = dense_index / tile_cells, cell = dense_index % tile_cells,
- *     element (tile, cell) at tile * tile_stride + cell (tile_stride >= tile_cells, padded to 32).
- *     dense_index is the reference's pattern number (pattern_utils.py:237-257).
+ *   - score tables live in a tiled device layout (kmerpapa_b200/csrc/kp_tables.h): the pattern table is
+ *     cut into tiles over a subset of positions, rows of a tile are stored in schedule order.  The
+ *     reference's dense pattern number (pattern_utils.py:237-257) is the external numbering everywhere
+ *     in this API; kp_gather_table / kp_gather_kept / kp_split_codes translate.
  *   - a plan is bound to one device and one general pattern; it is not thread-safe, different
  *     plans may be used from different threads.
  */
@@ -44,15 +46,19 @@ typedef struct kp_plan_info {
     uint64_t npat;           /* number of patterns = prod radix_i (pattern_utils.py:587-599) */
     uint64_t nkmer;          /* number of k-mers matched by the general pattern */
     uint64_t ntiles;         /* npat / tile_cells */
-    uint64_t table_elems;    /* ntiles * tile_stride: elements of d_best / d_split / d_tt */
+    uint64_t table_elems;    /* ntiles * tile_stride: float elements of d_best / d_train / d_test */
+    uint64_t kept_elems;     /* ntiles * rows (padded): uint16 elements of d_kept */
     uint64_t expanded_elems; /* ntiles * tile_kmers: elements of each expanded count table */
     uint64_t backtrack_ws_bytes; /* bytes of device workspace kp_backtrack needs for `cap` = 65536 */
     uint32_t k;              /* pattern length */
     uint32_t nlevels;        /* pattern_level(gen_pat) + 1 */
-    uint32_t tile_cells;     /* patterns per tile (product of the radices of the low positions) */
-    uint32_t tile_stride;    /* padded tile pitch in elements */
-    uint32_t tile_kmers;     /* k-mers spanned by the low positions */
+    uint32_t tile_cells;     /* patterns per tile (product of the radices of the on-chip positions) */
+    uint32_t tile_stride;    /* tile pitch in float elements */
+    uint32_t tile_kmers;     /* k-mers spanned by the on-chip positions */
     uint32_t low_positions;  /* number of (non-fixed) positions kept on chip */
+    uint32_t register_radix; /* radix of the position held in registers (15 for N) */
+    uint32_t rows, rounds;   /* rows per tile and rounds of the row schedule */
+    uint32_t warps_per_cta;  /* tiles in flight per SM for the single DP */
     uint32_t high_levels;    /* number of tile waves = launches of the DP kernel */
     uint32_t sm_count;
 } kp_plan_info;
@@ -79,31 +85,46 @@ int kp_expand_counts(kp_plan *plan, const int64_t *d_kmerM, const int64_t *d_kme
                      int64_t *d_expU, void *stream);
 
 /*
- * K3+K4.  Full DP.  d_best: float32[table_elems] best loss per pattern; d_split: uint8[table_elems],
- * position*8 + split_index of the winning two-way split, 0xFF when the pattern is kept whole.
+ * K3+K4.  Full DP.  d_best: float32[table_elems] best loss per pattern; d_kept: uint16[kept_elems], one
+ * bit per pattern, set when the pattern is kept whole (its own score beat every split).  Which split won
+ * is not stored: it is the first split in the reference's scan order whose float32 child sum equals the
+ * minimum, and kp_backtrack / kp_split_codes re-derive it from d_best.
  * max_count: upper bound of any pattern count (n_mut + n_unmut); selects 32- or 64-bit on-chip counts.
  */
 int kp_dp_single(kp_plan *plan, const int64_t *d_expM, const int64_t *d_expU, uint64_t max_count, double alpha,
-                 double beta, double penalty, float *d_best, uint8_t *d_split, void *stream);
+                 double beta, double penalty, float *d_best, uint16_t *d_kept, void *stream);
 
 /*
  * K5.  Partition of the general pattern, dense pattern numbers in the reference's emission order.
  * d_ws: device workspace of kp_backtrack_ws_bytes(cap).  Synchronises `stream`.
  */
 uint64_t kp_backtrack_ws_bytes(uint64_t cap);
-int kp_backtrack(kp_plan *plan, const uint8_t *d_split, void *d_ws, uint64_t cap, uint64_t *h_patnums,
-                 uint64_t *n_out, void *stream);
+int kp_backtrack(kp_plan *plan, const float *d_best, const uint16_t *d_kept, void *d_ws, uint64_t cap,
+                 uint64_t *h_patnums, uint64_t *n_out, void *stream);
+
+/*
+ * The reference's backtrack pointer as a code: h_codes[i] = 0xFF if pattern h_patnums[i] is kept whole, else
+ * position*8 + split_index of the winning split (bottum_up_array_w_numba.py:36-49).  Synchronises.
+ */
+int kp_split_codes(kp_plan *plan, const float *d_best, const uint16_t *d_kept, const uint64_t *h_patnums, uint64_t n,
+                   uint8_t *h_codes, void *stream);
+
+/* h_out[i] = table[first + i] for i < n, in dense pattern numbering (table: d_best / d_train / d_test). */
+int kp_gather_table(kp_plan *plan, const float *d_table, uint64_t first, uint64_t n, float *h_out, void *stream);
+/* h_out[i] = 1 if pattern first + i is kept whole. */
+int kp_gather_kept(kp_plan *plan, const uint16_t *d_kept, uint64_t first, uint64_t n, uint8_t *h_out, void *stream);
 
 /*
  * One cross-validation job = one fold x alpha x penalty.  d_exp?tot: all-fold totals, d_exp?test: the
  * fold's held-out counts (both from kp_expand_counts); train counts are formed on device as
- * total - held-out.  d_tt: float32[2 * table_elems], (train, test) interleaved per pattern.
+ * total - held-out.  d_train, d_test: float32[table_elems] each: training loss of the best partition of
+ * every pattern and the held-out loss of that same partition.
  * h_top[2]: train and held-out loss of the general pattern (written after synchronising `stream`);
  * may be NULL to leave the result on the device and not synchronise.
  */
 int kp_dp_cv_job(kp_plan *plan, const int64_t *d_expMtot, const int64_t *d_expUtot, const int64_t *d_expMtest,
                  const int64_t *d_expUtest, uint64_t max_count, double alpha, double beta_fold, double penalty,
-                 float *d_tt, float *h_top, void *stream);
+                 float *d_train, float *d_test, float *h_top, void *stream);
 
 /* Counts of arbitrary patterns (dense numbers) straight from the k-mer tables.  Synchronises. */
 int kp_pattern_counts(kp_plan *plan, const int64_t *d_kmerM, const int64_t *d_kmerU, const uint64_t *h_patnums,

@@ -14,11 +14,12 @@ class KpError(RuntimeError):
 class PlanInfo(ctypes.Structure):
     _fields_ = [
         ("npat", ctypes.c_uint64), ("nkmer", ctypes.c_uint64), ("ntiles", ctypes.c_uint64),
-        ("table_elems", ctypes.c_uint64), ("expanded_elems", ctypes.c_uint64),
+        ("table_elems", ctypes.c_uint64), ("kept_elems", ctypes.c_uint64), ("expanded_elems", ctypes.c_uint64),
         ("backtrack_ws_bytes", ctypes.c_uint64),
         ("k", ctypes.c_uint32), ("nlevels", ctypes.c_uint32), ("tile_cells", ctypes.c_uint32),
         ("tile_stride", ctypes.c_uint32), ("tile_kmers", ctypes.c_uint32), ("low_positions", ctypes.c_uint32),
-        ("high_levels", ctypes.c_uint32), ("sm_count", ctypes.c_uint32),
+        ("register_radix", ctypes.c_uint32), ("rows", ctypes.c_uint32), ("rounds", ctypes.c_uint32),
+        ("warps_per_cta", ctypes.c_uint32), ("high_levels", ctypes.c_uint32), ("sm_count", ctypes.c_uint32),
     ]
 
 
@@ -35,8 +36,11 @@ SYMBOLS = {
     "kp_expand_counts": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "kp_dp_single": (_int, [_vp, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
     "kp_backtrack_ws_bytes": (_u64, [_u64]),
-    "kp_backtrack": (_int, [_vp, _vp, _vp, _u64, _vp, ctypes.POINTER(_u64), _vp]),
-    "kp_dp_cv_job": (_int, [_vp, _vp, _vp, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
+    "kp_backtrack": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, ctypes.POINTER(_u64), _vp]),
+    "kp_split_codes": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp]),
+    "kp_gather_table": (_int, [_vp, _vp, _u64, _u64, _vp, _vp]),
+    "kp_gather_kept": (_int, [_vp, _vp, _u64, _u64, _vp, _vp]),
+    "kp_dp_cv_job": (_int, [_vp, _vp, _vp, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp]),
     "kp_pattern_counts": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp]),
     "kp_plan_launch_count": (_u64, [_vp]),
     "kp_debug_log": (_int, [_int, _vp, _vp, _u64]),

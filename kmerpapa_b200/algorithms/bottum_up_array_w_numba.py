@@ -39,8 +39,8 @@ def partition_from_arrays(gen_pat, codes, pos, neg, alpha, beta, penalty, device
     kM, kU = plan.pack_counts(codes, pos, neg)
     eM, eU = plan.expand(kM, kU)
     max_count = int(pos.sum()) + int(neg.sum())
-    best, split = plan.dp_single(eM, eU, max_count, alpha, beta, penalty)
-    patnums = plan.backtrack(split)
+    best, kept = plan.dp_single(eM, eU, max_count, alpha, beta, penalty)
+    patnums = plan.backtrack(best, kept)
     loss = plan.top_score(best)
     if want_counts:
         return loss, patnums, plan.pattern_counts(kM, kU, patnums)

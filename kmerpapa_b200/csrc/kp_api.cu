@@ -35,24 +35,47 @@ struct kp_plan {
     int device = 0;
     int sm_count = 0;
     KpTables *d_tab = nullptr;
-    uint32_t *d_cells = nullptr;
+    uint8_t *d_rowtab = nullptr;
     uint32_t *d_tiles = nullptr;
     uint8_t *d_genmask = nullptr;
     int *d_err = nullptr;
     uint64_t launches = 0;
-    int occ[2][2] = {{0, 0}, {0, 0}};  // resident CTAs per SM of the DP kernel [cv][wide]
+    int nwarps[2][2] = {{0, 0}, {0, 0}};  // warps (= tiles in flight) per CTA of the DP kernel [cv][wide]
     size_t smem[2][2] = {{0, 0}, {0, 0}};
+    size_t smem_optin = 0;
 };
+
+template <bool CV, bool WIDE>
+static const void *dp_kernel_for_radix(int r0)
+{
+    switch (r0) {
+    case 1: return (const void *)kp_dp_rows_kernel<1, CV, WIDE>;
+    case 3: return (const void *)kp_dp_rows_kernel<3, CV, WIDE>;
+    case 7: return (const void *)kp_dp_rows_kernel<7, CV, WIDE>;
+    default: return (const void *)kp_dp_rows_kernel<15, CV, WIDE>;
+    }
+}
+template <int R0>
+static void launch_dp_r0(bool cv, bool wide, int grid, int threads, size_t smem, cudaStream_t st, const KpDpParams &prm)
+{
+    if (!cv) {
+        if (wide) kp_dp_rows_kernel<R0, false, true><<<grid, threads, smem, st>>>(prm);
+        else kp_dp_rows_kernel<R0, false, false><<<grid, threads, smem, st>>>(prm);
+    } else {
+        if (wide) kp_dp_rows_kernel<R0, true, true><<<grid, threads, smem, st>>>(prm);
+        else kp_dp_rows_kernel<R0, true, false><<<grid, threads, smem, st>>>(prm);
+    }
+}
 
 extern "C" {
 
 const char *kp_last_error(void) { return g_err.c_str(); }
 int kp_version(void) { return 100; }
 
-static const void *dp_kernel_ptr(bool cv, bool wide)
+static const void *dp_kernel_ptr(int r0, bool cv, bool wide)
 {
-    if (!cv) return wide ? (const void *)kp_dp_wave_kernel<false, true> : (const void *)kp_dp_wave_kernel<false, false>;
-    return wide ? (const void *)kp_dp_wave_kernel<true, true> : (const void *)kp_dp_wave_kernel<true, false>;
+    if (!cv) return wide ? dp_kernel_for_radix<false, true>(r0) : dp_kernel_for_radix<false, false>(r0);
+    return wide ? dp_kernel_for_radix<true, true>(r0) : dp_kernel_for_radix<true, false>(r0);
 }
 
 int kp_plan_create(const char *gen_pat, int device, kp_plan **out)
@@ -74,25 +97,25 @@ int kp_plan_create(const char *gen_pat, int device, kp_plan **out)
     const KpTables &t = p->host.t;
     KP_CUDA(cudaMalloc(&p->d_tab, sizeof(KpTables)));
     KP_CUDA(cudaMemcpy(p->d_tab, &t, sizeof(KpTables), cudaMemcpyHostToDevice));
-    KP_CUDA(cudaMalloc(&p->d_cells, sizeof(uint32_t) * p->host.cell_list.size()));
-    KP_CUDA(cudaMemcpy(p->d_cells, p->host.cell_list.data(), sizeof(uint32_t) * p->host.cell_list.size(), cudaMemcpyHostToDevice));
+    KP_CUDA(cudaMalloc(&p->d_rowtab, p->host.rowtab.size()));
+    KP_CUDA(cudaMemcpy(p->d_rowtab, p->host.rowtab.data(), p->host.rowtab.size(), cudaMemcpyHostToDevice));
     KP_CUDA(cudaMalloc(&p->d_tiles, sizeof(uint32_t) * p->host.tile_order.size()));
     KP_CUDA(cudaMemcpy(p->d_tiles, p->host.tile_order.data(), sizeof(uint32_t) * p->host.tile_order.size(), cudaMemcpyHostToDevice));
     KP_CUDA(cudaMalloc(&p->d_genmask, KP_MAXK));
     KP_CUDA(cudaMemcpy(p->d_genmask, p->host.gen_mask, KP_MAXK, cudaMemcpyHostToDevice));
     KP_CUDA(cudaMalloc(&p->d_err, sizeof(int)));
     KP_CUDA(cudaMemset(p->d_err, 0, sizeof(int)));
+    p->smem_optin = prop.sharedMemPerBlockOptin;
     for (int cv = 0; cv < 2; cv++)
         for (int wide = 0; wide < 2; wide++) {
-            size_t sm = kp_dp_smem_bytes(cv, wide, t.tile_cells, t.tile_stride, t.nlow);
-            p->smem[cv][wide] = sm;
-            if (sm > (size_t)prop.sharedMemPerBlockOptin) { p->occ[cv][wide] = 0; continue; }
-            const void *fn = dp_kernel_ptr(cv, wide);
+            size_t fixed = 2048 + t.rt_bytes, per_warp = t.warp_smem_bytes[cv][wide];
+            int nw = fixed < p->smem_optin ? (int)((p->smem_optin - fixed) / per_warp) : 0;
+            if (nw > KP_MAX_WARPS) nw = KP_MAX_WARPS;
+            p->nwarps[cv][wide] = nw;
+            p->smem[cv][wide] = fixed + (size_t)nw * per_warp;
             // the attribute is per function, not per plan: always raise it to the device maximum
-            KP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
-            int nb = 0;
-            KP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, KP_NT, sm));
-            p->occ[cv][wide] = nb;
+            KP_CUDA(cudaFuncSetAttribute(dp_kernel_ptr(t.r0, cv, wide), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)prop.sharedMemPerBlockOptin));
         }
     *out = p;
     return 0;
@@ -103,7 +126,7 @@ int kp_plan_destroy(kp_plan *p)
     if (!p) return 0;
     cudaSetDevice(p->device);
     cudaFree(p->d_tab);
-    cudaFree(p->d_cells);
+    cudaFree(p->d_rowtab);
     cudaFree(p->d_tiles);
     cudaFree(p->d_genmask);
     cudaFree(p->d_err);
@@ -122,6 +145,7 @@ int kp_plan_get_info(const kp_plan *p, kp_plan_info *o)
     o->nkmer = p->host.nkmer;
     o->ntiles = t.ntiles;
     o->table_elems = (uint64_t)t.ntiles * t.tile_stride;
+    o->kept_elems = (uint64_t)t.ntiles * (uint64_t)t.rp;
     o->expanded_elems = (uint64_t)t.ntiles * t.tile_kmers;
     o->backtrack_ws_bytes = kp_backtrack_ws_bytes(65536);
     o->k = (uint32_t)p->host.k;
@@ -130,6 +154,10 @@ int kp_plan_get_info(const kp_plan *p, kp_plan_info *o)
     o->tile_stride = t.tile_stride;
     o->tile_kmers = t.tile_kmers;
     o->low_positions = (uint32_t)t.nlow;
+    o->register_radix = (uint32_t)t.r0;
+    o->rows = (uint32_t)t.nrows;
+    o->rounds = (uint32_t)t.nrounds;
+    o->warps_per_cta = (uint32_t)p->nwarps[0][0];
     o->high_levels = (uint32_t)(p->host.hl_off.size() - 1);
     o->sm_count = (uint32_t)p->sm_count;
     return 0;
@@ -190,8 +218,8 @@ int kp_expand_counts(kp_plan *p, const int64_t *d_kmerM, const int64_t *d_kmerU,
         p->d_tab, p->host.nkmer, (const long long *)d_kmerM, (const long long *)d_kmerU, (long long *)d_expM, (long long *)d_expU);
     p->launches++;
     uint64_t total = (uint64_t)t.ntiles * t.tile_kmers;
-    for (int e = t.nlow; e < t.npos; e++) {
-        kp_expand_pass_kernel<<<grid_for(total, 256, p->sm_count), 256, 0, st>>>(p->d_tab, e, (long long *)d_expM, (long long *)d_expU);
+    for (int hi = 0; hi < t.nhigh; hi++) {
+        kp_expand_pass_kernel<<<grid_for(total, 256, p->sm_count), 256, 0, st>>>(p->d_tab, hi, (long long *)d_expM, (long long *)d_expU);
         p->launches++;
     }
     KP_CUDA(cudaGetLastError());
@@ -200,25 +228,32 @@ int kp_expand_counts(kp_plan *p, const int64_t *d_kmerM, const int64_t *d_kmerU,
 
 static int launch_dp(kp_plan *p, bool cv, bool wide, KpDpParams prm, cudaStream_t st)
 {
-    int occ = p->occ[cv][wide];
-    if (occ < 1) return fail("DP kernel does not fit in shared memory for this tile shape");
+    int nw = p->nwarps[cv][wide];
+    if (nw < 1) return fail("DP kernel does not fit in shared memory for this tile shape");
     size_t smem = p->smem[cv][wide];
     size_t nhl = p->host.hl_off.size() - 1;
+    const int r0 = p->host.t.r0;
     for (size_t l = 0; l < nhl; l++) {
         uint64_t lo = p->host.hl_off[l], hi = p->host.hl_off[l + 1];
         if (hi == lo) continue;
         prm.tile_list = p->d_tiles + lo;
         prm.ntiles_wave = (uint32_t)(hi - lo);
         prm.leaf_wave = (l == 0);
-        uint64_t grid = hi - lo;
-        uint64_t cap = (uint64_t)p->sm_count * occ;
-        if (grid > cap) grid = cap;
-        if (!cv) {
-            if (wide) kp_dp_wave_kernel<false, true><<<(int)grid, KP_NT, smem, st>>>(prm);
-            else kp_dp_wave_kernel<false, false><<<(int)grid, KP_NT, smem, st>>>(prm);
-        } else {
-            if (wide) kp_dp_wave_kernel<true, true><<<(int)grid, KP_NT, smem, st>>>(prm);
-            else kp_dp_wave_kernel<true, false><<<(int)grid, KP_NT, smem, st>>>(prm);
+        uint64_t ntile = hi - lo;
+        int warps = nw;
+        if (ntile < (uint64_t)p->sm_count * nw) {  // small wave: spread the tiles over all SMs
+            warps = (int)((ntile + p->sm_count - 1) / p->sm_count);
+            if (warps < 1) warps = 1;
+        }
+        uint64_t grid = (ntile + warps - 1) / warps;
+        if (grid > (uint64_t)p->sm_count) grid = p->sm_count;
+        size_t sm = 2048 + p->host.t.rt_bytes + (size_t)warps * p->host.t.warp_smem_bytes[cv][wide];
+        (void)smem;
+        switch (r0) {
+        case 1: launch_dp_r0<1>(cv, wide, (int)grid, warps * 32, sm, st, prm); break;
+        case 3: launch_dp_r0<3>(cv, wide, (int)grid, warps * 32, sm, st, prm); break;
+        case 7: launch_dp_r0<7>(cv, wide, (int)grid, warps * 32, sm, st, prm); break;
+        default: launch_dp_r0<15>(cv, wide, (int)grid, warps * 32, sm, st, prm); break;
         }
         p->launches++;
     }
@@ -227,52 +262,56 @@ static int launch_dp(kp_plan *p, bool cv, bool wide, KpDpParams prm, cudaStream_
 }
 
 int kp_dp_single(kp_plan *p, const int64_t *d_expM, const int64_t *d_expU, uint64_t max_count, double alpha, double beta,
-                 double penalty, float *d_best, uint8_t *d_split, void *stream)
+                 double penalty, float *d_best, uint16_t *d_kept, void *stream)
 {
     if (!p) return fail("kp_dp_single: null plan");
     KP_CUDA(cudaSetDevice(p->device));
     KpDpParams prm;
     memset(&prm, 0, sizeof prm);
     prm.tab = p->d_tab;
-    prm.cell_list = p->d_cells;
+    prm.rowtab = p->d_rowtab;
     prm.e0 = (const long long *)d_expM;
     prm.e1 = (const long long *)d_expU;
     prm.alpha = alpha; prm.beta = beta; prm.penalty = penalty;
     prm.best = d_best;
-    prm.split = d_split;
+    prm.flags = d_kept;
     bool wide = max_count > 0xFFFFFFFFull;
     return launch_dp(p, false, wide, prm, (cudaStream_t)stream);
 }
 
 int kp_dp_cv_job(kp_plan *p, const int64_t *d_expMtot, const int64_t *d_expUtot, const int64_t *d_expMtest,
-                 const int64_t *d_expUtest, uint64_t max_count, double alpha, double beta_fold, double penalty, float *d_tt,
-                 float *h_top, void *stream)
+                 const int64_t *d_expUtest, uint64_t max_count, double alpha, double beta_fold, double penalty,
+                 float *d_train, float *d_test, float *h_top, void *stream)
 {
     if (!p) return fail("kp_dp_cv_job: null plan");
     KP_CUDA(cudaSetDevice(p->device));
     KpDpParams prm;
     memset(&prm, 0, sizeof prm);
     prm.tab = p->d_tab;
-    prm.cell_list = p->d_cells;
+    prm.rowtab = p->d_rowtab;
     prm.e0 = (const long long *)d_expMtot;
     prm.e1 = (const long long *)d_expUtot;
     prm.e2 = (const long long *)d_expMtest;
     prm.e3 = (const long long *)d_expUtest;
     prm.alpha = alpha; prm.beta = beta_fold; prm.penalty = penalty;
-    prm.tt = d_tt;
+    prm.best = d_train;
+    prm.test = d_test;
     bool wide = max_count > 0xFFFFFFFFull;
     if (launch_dp(p, true, wide, prm, (cudaStream_t)stream)) return 1;
     if (h_top) {
+        uint64_t tile; uint32_t srow, d0;
+        kp_locate(p->host, p->host.npat - 1, &tile, &srow, &d0);
         const KpTables &t = p->host.t;
-        size_t top = ((size_t)(t.ntiles - 1) * t.tile_stride + (t.tile_cells - 1)) * 2;
-        KP_CUDA(cudaMemcpyAsync(h_top, d_tt + top, 2 * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        size_t top = (size_t)tile * t.tile_stride + ((size_t)(d0 >> 2) * t.rp + srow) * 4 + (d0 & 3);
+        KP_CUDA(cudaMemcpyAsync(h_top, d_train + top, sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        KP_CUDA(cudaMemcpyAsync(h_top + 1, d_test + top, sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
         KP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     }
     return 0;
 }
 
-int kp_backtrack(kp_plan *p, const uint8_t *d_split, void *d_ws, uint64_t cap, uint64_t *h_patnums, uint64_t *n_out,
-                 void *stream)
+int kp_backtrack(kp_plan *p, const float *d_best, const uint16_t *d_kept, void *d_ws, uint64_t cap, uint64_t *h_patnums,
+                 uint64_t *n_out, void *stream)
 {
     if (!p || !d_ws || !h_patnums || !n_out) return fail("kp_backtrack: null argument");
     if (p->host.t.total_level > 64) return fail("kp_backtrack: more than 64 levels");
@@ -281,7 +320,7 @@ int kp_backtrack(kp_plan *p, const uint8_t *d_split, void *d_ws, uint64_t cap, u
     KpBtNode *fa = (KpBtNode *)d_ws, *fb = fa + cap, *leaves = fb + cap;
     unsigned long long *sorted = (unsigned long long *)(leaves + cap);
     unsigned long long *counts = sorted + cap;
-    kp_backtrack_kernel<<<1, 256, 0, st>>>(p->d_tab, d_split, p->host.npat - 1, fa, fb, leaves, cap, counts);
+    kp_backtrack_kernel<<<1, 256, 0, st>>>(p->d_tab, p->d_rowtab, d_best, d_kept, p->host.npat - 1, fa, fb, leaves, cap, counts);
     p->launches++;
     KP_CUDA(cudaGetLastError());
     unsigned long long hc[2] = {0, 0};
@@ -293,6 +332,62 @@ int kp_backtrack(kp_plan *p, const uint8_t *d_split, void *d_ws, uint64_t cap, u
     p->launches++;
     KP_CUDA(cudaGetLastError());
     KP_CUDA(cudaMemcpyAsync(h_patnums, sorted, hc[0] * 8, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int kp_split_codes(kp_plan *p, const float *d_best, const uint16_t *d_kept, const uint64_t *h_patnums, uint64_t n,
+                   uint8_t *h_codes, void *stream)
+{
+    if (!p) return fail("kp_split_codes: null plan");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    KP_CUDA(cudaSetDevice(p->device));
+    unsigned long long *d_pat = nullptr;
+    uint8_t *d_codes = nullptr;
+    KP_CUDA(cudaMallocAsync(&d_pat, n * 8, st));
+    KP_CUDA(cudaMallocAsync(&d_codes, n, st));
+    KP_CUDA(cudaMemcpyAsync(d_pat, h_patnums, n * 8, cudaMemcpyHostToDevice, st));
+    kp_split_codes_kernel<<<grid_for(n, 256, p->sm_count), 256, 0, st>>>(p->d_tab, p->d_rowtab, d_best, d_kept, d_pat, n, d_codes);
+    p->launches++;
+    KP_CUDA(cudaGetLastError());
+    KP_CUDA(cudaMemcpyAsync(h_codes, d_codes, n, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaFreeAsync(d_pat, st));
+    KP_CUDA(cudaFreeAsync(d_codes, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int kp_gather_table(kp_plan *p, const float *d_table, uint64_t first, uint64_t n, float *h_out, void *stream)
+{
+    if (!p) return fail("kp_gather_table: null plan");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    KP_CUDA(cudaSetDevice(p->device));
+    float *d_out = nullptr;
+    KP_CUDA(cudaMallocAsync(&d_out, n * 4, st));
+    kp_gather_kernel<<<grid_for(n, 256, p->sm_count), 256, 0, st>>>(p->d_tab, p->d_rowtab, d_table, nullptr, first, n, d_out);
+    p->launches++;
+    KP_CUDA(cudaGetLastError());
+    KP_CUDA(cudaMemcpyAsync(h_out, d_out, n * 4, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaFreeAsync(d_out, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int kp_gather_kept(kp_plan *p, const uint16_t *d_kept, uint64_t first, uint64_t n, uint8_t *h_out, void *stream)
+{
+    if (!p) return fail("kp_gather_kept: null plan");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    KP_CUDA(cudaSetDevice(p->device));
+    uint8_t *d_out = nullptr;
+    KP_CUDA(cudaMallocAsync(&d_out, n, st));
+    kp_gather_flags_kernel<<<grid_for(n, 256, p->sm_count), 256, 0, st>>>(p->d_tab, p->d_rowtab, d_kept, first, n, d_out);
+    p->launches++;
+    KP_CUDA(cudaGetLastError());
+    KP_CUDA(cudaMemcpyAsync(h_out, d_out, n, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaFreeAsync(d_out, st));
     KP_CUDA(cudaStreamSynchronize(st));
     return 0;
 }

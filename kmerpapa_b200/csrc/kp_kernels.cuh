@@ -1,18 +1,19 @@
 // kp_kernels.cuh — sm_100a kernels of the pattern-partition DP.
 //
-// Data layout: the pattern table is cut into tiles of `tile_cells` consecutive dense
-// pattern numbers (the low positions of the general pattern); a tile is identified by the digits of the
-// remaining (high) positions.  One CTA owns one tile at a time:
-//   phase A  list the tile's high-position splits (two child tiles each, same cell offset)
-//   phase B  load the tile's low-k-mer counts and expand them to all cells in shared memory
-//            (subset sums, one pass per low position: each pattern = sum of disjoint sub-patterns)
-//   phase C  float64 self-score of every cell (glibc-exact log), kept in shared memory
-//   phase D  stream the child tiles from HBM/L2 with 16-byte coalesced loads, keep the running
-//            (min, first rank) of f32(best[c1] + best[c2]) per cell
-//   phase E  wavefront over the tile's own levels in shared memory: low-position splits, merge with the
-//            streamed minimum, compare with the self-score (float64 compare, float32 store)
-//   phase F  write the tile's best scores and split codes once
-// Tiles of one "high level" (sum of the levels of the high digits) are independent: one launch per level.
+// Work decomposition (geometry in kp_tables.h, rationale in DESIGN.md):
+//   * one WARP owns one tile at a time, one LANE owns one row of it, and the r0 (<= 15) sub-patterns of
+//     the register position of that row live in registers v[0..r0).  No block-wide barrier in steady state.
+//   * rows are visited in a precomputed schedule (rounds of <= 32 rows whose children are complete).
+//   * per row:  counts of the row's base k-mers (shared memory, int) -> subset sums in registers;
+//               running minimum over the HIGH-position splits, streamed from two child tiles each with
+//               coalesced 16-byte loads (HBM/L2);
+//               running minimum over the CROSS-row splits, from the tile's finished rows in shared memory;
+//               in-register splits of the register position interleaved with the float64 self-score
+//               (glibc-exact log) and the float64 compare / float32 store of the reference;
+//               one coalesced 16-byte store per group to the table, one 16-bit "kept whole" mask per row.
+//   * the single DP only keeps the minimum (fminf); which split won is recomputed by the backtrack
+//     from the stored scores (first split in scan order that reproduces the minimum).  The CV job needs
+//     the held-out loss of the winning split, so it tracks (value, scan rank) lexicographically.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -20,103 +21,159 @@
 #include "kp_math.cuh"
 #include "kp_tables.h"
 
-#define KP_NT 256          // threads per CTA of the DP kernel
-#define KP_QPT 4           // 16-byte chunks per thread in the streaming phase (single DP)
+#define KP_MAX_WARPS 16
 
 struct KpDpParams {
     const KpTables *tab;
-    const uint32_t *cell_list;
+    const uint8_t *rowtab;
     const uint32_t *tile_list;  // tiles of this wave, ascending
     uint32_t ntiles_wave;
-    int leaf_wave;              // wave 0: cells of mini-level 0 are k-mers (level-0 formula)
-    const long long *e0, *e1, *e2, *e3;  // single: M, U.  CV: Mtot, Utot, Mtest, Utest
+    int leaf_wave;              // wave 0: rows of level 0 hold k-mers at the single-nucleotide digits
+    const long long *e0, *e1, *e2, *e3;  // single: M, U.  CV: Mtot, Utot, Mtest, Utest  [ntiles][tile_kmers]
     double alpha, beta, penalty;
-    float *best;        // single
-    uint8_t *split;     // single
-    float *tt;          // CV: (train, test) interleaved
+    float *best;        // single: best loss;  CV: train loss
+    float *test;        // CV: held-out loss of the chosen partition
+    uint16_t *flags;    // single: per row, bit d set = pattern kept whole
 };
 
-__host__ __device__ inline size_t kp_dp_smem_bytes(bool cv, bool wide, uint32_t cells, uint32_t stride, int nlow)
+template <bool WIDE> struct KpCnt { typedef unsigned int type; };
+template <> struct KpCnt<true> { typedef unsigned long long type; };
+
+__device__ __forceinline__ double kp_cnt2d(unsigned int x) { return __uint2double_rn(x); }
+__device__ __forceinline__ double kp_cnt2d(unsigned long long x) { return __ull2double_rn(x); }
+
+// level >= 1 self-score (w_numba.py:56-61 / _CV.py:60-70), templated on the on-chip count width
+template <typename C>
+__device__ __forceinline__ double kp_self_score_t(C M, C U, double alpha, double beta, double penalty,
+                                                  const double2 *tab, double &logp, double &log1mp)
 {
-    size_t ns = (size_t)(cv ? 2 : 1) * (wide ? 2 : 1);
-    size_t b = 2048;                         // log table
-    b += ns * stride * 8;                    // count slots, later self-scores
-    b += (size_t)(cv ? 2 : 1) * stride * 4;  // S (and T)
-    b += cv ? 0 : stride;                    // R
-    b += ((size_t)cells + 3) / 4 * 16;       // cell list
-    b += (size_t)nlow * 128 * 4;             // low split offsets
-    b += (size_t)nlow * 16;                  // low split counts
-    b += KP_MAXHS * 4 * 2 + 128;             // high split list
-    b += 32 * 4;                             // mini-level offsets
-    b += 16 + KP_MAXLOW * 4;                 // scalars, per-low-position meta
-    return b;
+    double Md = kp_cnt2d(M), Ud = kp_cnt2d(U);
+    double p = __ddiv_rn(KP_ADD(Md, alpha), KP_ADD(KP_ADD(kp_cnt2d((C)(M + U)), alpha), beta));
+    logp = kp_log(p, tab);
+    log1mp = kp_log(KP_SUB(1.0, p), tab);
+    double s = penalty;
+    if (M > 0) s = KP_ADD(s, KP_MUL(KP_MUL(-2.0, Md), logp));
+    if (U > 0) s = KP_ADD(s, KP_MUL(KP_MUL(-2.0, Ud), log1mp));
+    return s;
 }
 
-template <bool WIDE>
-__device__ __forceinline__ unsigned long long kp_ldcnt(const unsigned long long *slot, uint32_t stride, int which,
-                                                       uint32_t cell)
+// level-0 scores are rare (k-mers only): keep them out of line
+__device__ __noinline__ double kp_leaf_score_nl(unsigned long long M, unsigned long long U, double alpha, double beta,
+                                                double penalty, const double2 *tab)
 {
-    if (WIDE) return slot[(size_t)which * stride + cell];
-    return ((const uint32_t *)slot)[((size_t)(which >> 1) * stride + cell) * 2 + (which & 1)];
+    return kp_leaf_score(M, U, alpha, beta, penalty, tab);
 }
-template <bool WIDE>
-__device__ __forceinline__ void kp_stcnt(unsigned long long *slot, uint32_t stride, int which, uint32_t cell,
-                                         unsigned long long v)
+__device__ __noinline__ void kp_leaf_cv_nl(unsigned long long Mtr, unsigned long long Utr, unsigned long long Mte,
+                                           unsigned long long Ute, double alpha, double beta, double penalty,
+                                           const double2 *tab, double *train, double *test)
 {
-    if (WIDE) slot[(size_t)which * stride + cell] = v;
-    else ((uint32_t *)slot)[((size_t)(which >> 1) * stride + cell) * 2 + (which & 1)] = (uint32_t)v;
+    double a, b;
+    kp_leaf_cv(Mtr, Utr, Mte, Ute, alpha, beta, penalty, tab, a, b);
+    *train = a;
+    *test = b;
 }
 
-template <bool CV, bool WIDE>
-__global__ void __launch_bounds__(KP_NT) kp_dp_wave_kernel(const KpDpParams p)
+// ---------------------------------------------------------------------------------------------------
+// Per-row state and the in-register part of the recurrence.  Everything is indexed with compile-time
+// constants (macros below) so the arrays stay in registers.
+// ---------------------------------------------------------------------------------------------------
+template <int R0, bool CV, bool WIDE>
+struct KpRow {
+    typedef typename KpCnt<WIDE>::type C;
+    static constexpr int NB = R0 == 15 ? 4 : (R0 == 7 ? 3 : (R0 == 3 ? 2 : 1));
+    static constexpr int NG = (R0 + 3) / 4;
+    float v[NG * 4];        // best (train) loss so far / final
+    float tv[CV ? NG * 4 : 1];   // CV: held-out loss of the current winner
+    int rk[CV ? NG * 4 : 1];     // CV: scan rank of the current winner (pos*8+j), 0x7fffffff = none yet
+    C m[NB], u[NB];         // counts of the row at the single-nucleotide digits of the register position
+    C mt[CV ? NB : 1], ut[CV ? NB : 1];
+    uint32_t flag;
+};
+
+#define KP_NONE 0x7fffffff
+#define KP_FETCH 0x40000000  // CV: winner comes from a streamed or cross-row split; held-out value still to fetch
+
+template <int R0, bool CV, bool WIDE>
+struct KpRowOps {
+    typedef KpRow<R0, CV, WIDE> Row;
+    typedef typename Row::C C;
+
+    // one in-register split candidate of digit D with children A, B (J = split index in scan order)
+    template <int D, int A, int B, int J>
+    static __device__ __forceinline__ void split(Row &r, int rankbase)
+    {
+        float cand = __fadd_rn(r.v[A], r.v[B]);
+        if (!CV) {
+            r.v[D] = fminf(r.v[D], cand);
+        } else {
+            int rank = rankbase + J;
+            bool take = (cand < r.v[D]) || (cand == r.v[D] && rank < (r.rk[D] & ~KP_FETCH));
+            if (take) { r.v[D] = cand; r.rk[D] = rank; r.tv[D] = __fadd_rn(r.tv[A], r.tv[B]); }
+        }
+    }
+
+    // subset sum of the per-base counts for digit-space base mask BM
+    template <int BM>
+    static __device__ __forceinline__ C sum(const C *x)
+    {
+        C s = 0;
+#pragma unroll
+        for (int b = 0; b < Row::NB; b++)
+            if ((BM >> b) & 1) s += x[b];
+        return s;
+    }
+};
+
+template <int R0, bool CV, bool WIDE>
+__global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const KpDpParams p)
 {
+    typedef KpRow<R0, CV, WIDE> Row;
+    typedef KpRowOps<R0, CV, WIDE> Ops;
+    typedef typename Row::C C;
+    constexpr int NB = Row::NB, NG = Row::NG;
+    constexpr int CW = (CV ? 4 : 2);  // counters per base k-mer
+
     extern __shared__ __align__(16) unsigned char smem[];
     const KpTables &tb = *p.tab;
-    const int tid = threadIdx.x;
-    const uint32_t cells = tb.tile_cells, stride = tb.tile_stride, tk = tb.tile_kmers;
-    const int nlow = tb.nlow, npos = tb.npos, nml = tb.nml;
-    constexpr int NS = (CV ? 2 : 1) * (WIDE ? 2 : 1);
-    constexpr int NC = CV ? 4 : 2;  // logical counters per cell
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int rp = tb.rp, nrounds = tb.nrounds, nhigh = tb.nhigh;
+    const uint32_t tk = tb.tile_kmers, stride = tb.tile_stride;
+    const uint32_t rt_bytes = tb.rt_bytes;
 
     double2 *logtab = (double2 *)smem;
-    unsigned long long *slot = (unsigned long long *)(smem + 2048);
-    float *S = (float *)(slot + (size_t)NS * stride);
-    float *T = S + stride;                                    // CV only
-    uint8_t *R = (uint8_t *)(S + (size_t)(CV ? 2 : 1) * stride);  // single only
-    uint32_t *cl = (uint32_t *)(R + (CV ? 0 : stride));
-    int *lowd = (int *)(cl + ((cells + 3) / 4) * 4);
-    uint8_t *lowns = (uint8_t *)(lowd + nlow * 128);
-    uint32_t *hs1 = (uint32_t *)(lowns + nlow * 16);
+    unsigned char *rt = smem + 2048;
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) logtab[i] = make_double2(kpc_logTab[2 * i], kpc_logTab[2 * i + 1]);
+    for (uint32_t i = threadIdx.x; i < rt_bytes / 4; i += blockDim.x) ((uint32_t *)rt)[i] = ((const uint32_t *)p.rowtab)[i];
+    __syncthreads();
+    const uint16_t *round_start = (const uint16_t *)(rt + tb.rt_round_start);
+    const uint8_t *row_level = rt + tb.rt_row_level;
+    const uint16_t *xs_off = (const uint16_t *)(rt + tb.rt_xs_off);
+    const uint32_t *xs = (const uint32_t *)(rt + tb.rt_xs);
+    const uint8_t *xsr = rt + tb.rt_xs_rank;
+    const uint16_t *bs_off = (const uint16_t *)(rt + tb.rt_bs_off);
+    const uint16_t *bs = (const uint16_t *)(rt + tb.rt_bs);
+
+    unsigned char *wm = smem + 2048 + rt_bytes + (size_t)warp * tb.warp_smem_bytes[CV][WIDE];
+    float4 *S = (float4 *)wm;                                  // [NG][rp]
+    C *bc = (C *)(wm + (size_t)NG * rp * 16);                  // [tile_kmers][CW]
+    uint32_t *hs1 = (uint32_t *)((unsigned char *)bc + (size_t)tk * CW * sizeof(C));
     uint32_t *hs2 = hs1 + KP_MAXHS;
     uint8_t *hsr = (uint8_t *)(hs2 + KP_MAXHS);
-    uint32_t *mlo = (uint32_t *)(hsr + 128);
-    int *s_nhs = (int *)(mlo + 32);
-    uint32_t *lowmeta = (uint32_t *)(s_nhs + 4);  // shift | field mask << 8 | rank base << 16
-
-    // ---- once per CTA: stage the read-only tables ----
-    for (int i = tid; i < 128; i += KP_NT) logtab[i] = make_double2(kpc_logTab[2 * i], kpc_logTab[2 * i + 1]);
-    for (uint32_t i = tid; i < cells; i += KP_NT) cl[i] = p.cell_list[i];
-    for (int i = tid; i < nlow * 128; i += KP_NT) {
-        int e = i >> 7, d = (i >> 3) & 15, j = i & 7;
-        lowd[i] = (int)(((uint32_t)(uint16_t)tb.low_d1[e][d][j]) | ((uint32_t)(uint16_t)tb.low_d2[e][d][j] << 16));
-    }
-    for (int i = tid; i < nlow * 16; i += KP_NT) lowns[i] = tb.low_ns[i >> 4][i & 15];
-    for (int i = tid; i <= nml; i += KP_NT) mlo[i] = tb.ml_off[i];
-    for (int i = tid; i < nlow; i += KP_NT)
-        lowmeta[i] = (uint32_t)tb.shift[i] | ((uint32_t)tb.fmask[i] << 8) | ((uint32_t)tb.pos_id[i] * 8u << 16);
-    __syncthreads();
+    int *s_nhs = (int *)(hsr + KP_MAXHS);
 
     const double alpha = p.alpha, beta = p.beta, penalty = p.penalty;
     const float INF = __int_as_float(0x7f800000);
+    const int rankbase = tb.estar >= 0 ? tb.pos_id[tb.estar] * 8 : 0;
 
-    for (uint32_t it = blockIdx.x; it < p.ntiles_wave; it += gridDim.x) {
+    for (uint32_t it = blockIdx.x * nwarps + warp; it < p.ntiles_wave; it += gridDim.x * nwarps) {
         const uint32_t tile = p.tile_list[it];
-
-        // ---- phase A: the tile's high-position splits, in scan order (position, split) ----
-        if (tid < 32) {
-            int e = nlow + tid, ns = 0, d = 0;
+        __syncwarp();  // previous tile's readers of S / bc / hs are done
+        // ---- the tile's high-position splits, in scan order ----
+        {
+            int ns = 0, d = 0, e = 0;
             uint32_t m = 0, hw = 1;
-            if (e < npos) {
+            if (lane < nhigh) {
+                e = tb.highpos[lane];
                 hw = tb.highw[e];
                 d = (int)((tile / hw) % tb.radix[e]);
                 m = tb.digit_mask[e][d];
@@ -125,8 +182,8 @@ __global__ void __launch_bounds__(KP_NT) kp_dp_wave_kernel(const KpDpParams p)
             int off = ns;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                int v = __shfl_up_sync(0xffffffffu, off, o);
-                if (tid >= o) off += v;
+                int x = __shfl_up_sync(0xffffffffu, off, o);
+                if (lane >= o) off += x;
             }
             int total = __shfl_sync(0xffffffffu, off, 31);
             off -= ns;
@@ -136,200 +193,182 @@ __global__ void __launch_bounds__(KP_NT) kp_dp_wave_kernel(const KpDpParams p)
                 hs2[off + j] = tile - (uint32_t)(d - c2) * hw;
                 hsr[off + j] = (uint8_t)(tb.pos_id[e] * 8 + j);
             }
-            if (tid == 0) *s_nhs = total;
+            if (lane == 0) *s_nhs = total;
         }
-
-        // ---- phase B: counts.  k-mer cells first, then one subset-sum pass per low position ----
-        for (uint32_t kl = tid; kl < tk; kl += KP_NT) {
-            uint32_t cell = 0;
-            for (int e = 0; e < nlow; e++) cell += ((kl / tb.lowkw[e]) % tb.nbase[e]) * tb.loww[e];
+        // ---- base counts of the tile ----
+        for (uint32_t kl = lane; kl < tk; kl += 32) {
             size_t g = (size_t)tile * tk + kl;
             if (!CV) {
-                kp_stcnt<WIDE>(slot, stride, 0, cell, (unsigned long long)p.e0[g]);
-                kp_stcnt<WIDE>(slot, stride, 1, cell, (unsigned long long)p.e1[g]);
+                bc[kl * CW + 0] = (C)p.e0[g];
+                bc[kl * CW + 1] = (C)p.e1[g];
             } else {
                 long long mt = p.e2[g], ut = p.e3[g];
-                kp_stcnt<WIDE>(slot, stride, 0, cell, (unsigned long long)(p.e0[g] - mt));  // train = total - held-out
-                kp_stcnt<WIDE>(slot, stride, 1, cell, (unsigned long long)(p.e1[g] - ut));
-                kp_stcnt<WIDE>(slot, stride, 2, cell, (unsigned long long)mt);
-                kp_stcnt<WIDE>(slot, stride, 3, cell, (unsigned long long)ut);
+                bc[kl * CW + 0] = (C)(p.e0[g] - mt);  // train = total - held-out
+                bc[kl * CW + 1] = (C)(p.e1[g] - ut);
+                bc[kl * CW + 2] = (C)mt;
+                bc[kl * CW + 3] = (C)ut;
             }
         }
-        __syncthreads();
-        for (int e = 0; e < nlow; e++) {
-            const uint32_t sh = tb.shift[e], fm = tb.fmask[e], lw = tb.loww[e];
-            for (uint32_t i = tid; i < cells; i += KP_NT) {
-                uint32_t pk = cl[i];
-                if ((int)(pk >> 28) != e + 1) continue;  // highest multi-letter low position of this cell
-                uint32_t cell = (pk >> 16) & 0xFFFu;
-                int d = (int)((pk >> sh) & fm);
-                uint32_t m = tb.digit_mask[e][d];
-                unsigned long long acc[NC];
-#pragma unroll
-                for (int c = 0; c < NC; c++) acc[c] = 0;
-                for (int b = 0; b < 4; b++) {
-                    if (!((m >> b) & 1u)) continue;
-                    uint32_t src = cell - (uint32_t)(d - (int)tb.mask_digit[e][1u << b]) * lw;
-#pragma unroll
-                    for (int c = 0; c < NC; c++) acc[c] += kp_ldcnt<WIDE>(slot, stride, c, src);
-                }
-#pragma unroll
-                for (int c = 0; c < NC; c++) kp_stcnt<WIDE>(slot, stride, c, cell, acc[c]);
-            }
-            __syncthreads();
-        }
-
-        // ---- phase C: float64 self-score per cell; overwrites the cell's own counts ----
-        {
-            const uint32_t nleaf = p.leaf_wave ? mlo[1] : 0u;
-            float *tsl = (float *)(slot + (size_t)(WIDE ? 2 : 1) * stride);
-            for (uint32_t i = tid; i < cells; i += KP_NT) {
-                uint32_t cell = (cl[i] >> 16) & 0xFFFu;
-                unsigned long long M = kp_ldcnt<WIDE>(slot, stride, 0, cell), U = kp_ldcnt<WIDE>(slot, stride, 1, cell);
-                double s;
-                if (!CV) {
-                    if (i < nleaf) {
-                        s = (double)__double2float_rn(kp_leaf_score(M, U, alpha, beta, penalty, logtab));
-                    } else {
-                        double lp, l1;
-                        s = kp_self_score(M, U, alpha, beta, penalty, logtab, lp, l1);
-                    }
-                } else {
-                    unsigned long long Mt = kp_ldcnt<WIDE>(slot, stride, 2, cell), Ut = kp_ldcnt<WIDE>(slot, stride, 3, cell);
-                    double t;
-                    if (i < nleaf) {
-                        kp_leaf_cv(M, U, Mt, Ut, alpha, beta, penalty, logtab, s, t);
-                        s = (double)__double2float_rn(s);
-                    } else {
-                        double lp, l1;
-                        s = kp_self_score(M, U, alpha, beta, penalty, logtab, lp, l1);
-                        t = kp_test_ll(Mt, Ut, lp, l1);
-                    }
-                    tsl[2 * (size_t)cell] = __double2float_rn(t);
-                }
-                ((double *)slot)[cell] = s;
-            }
-        }
-        __syncthreads();  // hs list (phase A) visible; also orders phase C before phase E
-
-        // ---- phase D: stream the child tiles of the high-position splits ----
+        __syncwarp();
         const int nhs = *s_nhs;
-        if (!CV) {
-            const int nq = (int)((cells + 3) >> 2);
-            float4 hv[KP_QPT];
-            uint32_t hr[KP_QPT];
+        const float *tbase = p.best;
+        float4 *otile = (float4 *)(p.best + (size_t)tile * stride);
+
+        for (int rnd = 0; rnd < nrounds; rnd++) {
+            const int srow = round_start[rnd] + lane;
+            if (srow < round_start[rnd + 1]) {
+                Row r;
+                r.flag = 0;
+                // ---- counts of this row at the single-nucleotide digits ----
 #pragma unroll
-            for (int c = 0; c < KP_QPT; c++) { hv[c] = make_float4(INF, INF, INF, INF); hr[c] = 0xFFFFFFFFu; }
-            for (int s = 0; s < nhs; s++) {
-                const float4 *a = (const float4 *)(p.best + (size_t)hs1[s] * stride);
-                const float4 *b = (const float4 *)(p.best + (size_t)hs2[s] * stride);
-                const uint32_t rk = hsr[s];
+                for (int b = 0; b < NB; b++) { r.m[b] = 0; r.u[b] = 0; if (CV) { r.mt[b] = 0; r.ut[b] = 0; } }
+                for (int i = bs_off[srow]; i < bs_off[srow + 1]; i++) {
+                    const C *q = bc + (size_t)bs[i] * NB * CW;
 #pragma unroll
-                for (int c = 0; c < KP_QPT; c++) {
-                    int q = tid + c * KP_NT;
-                    if (q < nq) {
-                        float4 x = __ldg(a + q), y = __ldg(b + q);
-                        float v0 = __fadd_rn(x.x, y.x), v1 = __fadd_rn(x.y, y.y), v2 = __fadd_rn(x.z, y.z), v3 = __fadd_rn(x.w, y.w);
-                        if (v0 < hv[c].x) { hv[c].x = v0; hr[c] = (hr[c] & 0xFFFFFF00u) | rk; }
-                        if (v1 < hv[c].y) { hv[c].y = v1; hr[c] = (hr[c] & 0xFFFF00FFu) | (rk << 8); }
-                        if (v2 < hv[c].z) { hv[c].z = v2; hr[c] = (hr[c] & 0xFF00FFFFu) | (rk << 16); }
-                        if (v3 < hv[c].w) { hv[c].w = v3; hr[c] = (hr[c] & 0x00FFFFFFu) | (rk << 24); }
+                    for (int b = 0; b < NB; b++) {
+                        r.m[b] += q[b * CW + 0];
+                        r.u[b] += q[b * CW + 1];
+                        if (CV) { r.mt[b] += q[b * CW + 2]; r.ut[b] += q[b * CW + 3]; }
                     }
                 }
-            }
 #pragma unroll
-            for (int c = 0; c < KP_QPT; c++) {
-                int q = tid + c * KP_NT;
-                if (q < nq) { ((float4 *)S)[q] = hv[c]; ((uint32_t *)R)[q] = hr[c]; }
-            }
-        } else {
-            const int nq = (int)((cells + 1) >> 1);  // 16 bytes = 2 cells x (train, test)
-            for (int q0 = tid; q0 < nq; q0 += KP_NT * KP_QPT) {
-                float2 hv[KP_QPT], ht[KP_QPT];
-#pragma unroll
-                for (int c = 0; c < KP_QPT; c++) { hv[c] = make_float2(INF, INF); ht[c] = make_float2(0.f, 0.f); }
+                for (int c = 0; c < NG * 4; c++) { r.v[c] = INF; if (CV) { r.tv[c] = 0.f; r.rk[c] = KP_NONE; } }
+
+                // ---- high-position splits: stream two child tiles per split ----
                 for (int s = 0; s < nhs; s++) {
-                    const float4 *a = (const float4 *)(p.tt + (size_t)hs1[s] * stride * 2);
-                    const float4 *b = (const float4 *)(p.tt + (size_t)hs2[s] * stride * 2);
+                    const float4 *a = (const float4 *)(tbase + (size_t)hs1[s] * stride) + srow;
+                    const float4 *b = (const float4 *)(tbase + (size_t)hs2[s] * stride) + srow;
+                    float4 xa[NG], xb[NG];
 #pragma unroll
-                    for (int c = 0; c < KP_QPT; c++) {
-                        int q = q0 + c * KP_NT;
-                        if (q < nq) {
-                            float4 x = __ldg(a + q), y = __ldg(b + q);
-                            float v0 = __fadd_rn(x.x, y.x), v1 = __fadd_rn(x.z, y.z);
-                            if (v0 < hv[c].x) { hv[c].x = v0; ht[c].x = __fadd_rn(x.y, y.y); }
-                            if (v1 < hv[c].y) { hv[c].y = v1; ht[c].y = __fadd_rn(x.w, y.w); }
+                    for (int g = 0; g < NG; g++) { xa[g] = __ldg(a + g * rp); xb[g] = __ldg(b + g * rp); }
+                    const int rank = CV ? (int)hsr[s] : 0;
+#pragma unroll
+                    for (int g = 0; g < NG; g++) {
+                        float c0 = __fadd_rn(xa[g].x, xb[g].x), c1 = __fadd_rn(xa[g].y, xb[g].y);
+                        float c2 = __fadd_rn(xa[g].z, xb[g].z), c3 = __fadd_rn(xa[g].w, xb[g].w);
+                        if (!CV) {
+                            r.v[4 * g + 0] = fminf(r.v[4 * g + 0], c0);
+                            r.v[4 * g + 1] = fminf(r.v[4 * g + 1], c1);
+                            r.v[4 * g + 2] = fminf(r.v[4 * g + 2], c2);
+                            r.v[4 * g + 3] = fminf(r.v[4 * g + 3], c3);
+                        } else {
+                            // hs is in scan order: a strict '<' keeps the earliest split among equals
+                            if (c0 < r.v[4 * g + 0]) { r.v[4 * g + 0] = c0; r.rk[4 * g + 0] = rank | KP_FETCH; }
+                            if (c1 < r.v[4 * g + 1]) { r.v[4 * g + 1] = c1; r.rk[4 * g + 1] = rank | KP_FETCH; }
+                            if (c2 < r.v[4 * g + 2]) { r.v[4 * g + 2] = c2; r.rk[4 * g + 2] = rank | KP_FETCH; }
+                            if (c3 < r.v[4 * g + 3]) { r.v[4 * g + 3] = c3; r.rk[4 * g + 3] = rank | KP_FETCH; }
                         }
                     }
                 }
+                // ---- cross-row splits: finished rows of this tile, shared memory ----
+                for (int i = xs_off[srow]; i < xs_off[srow + 1]; i++) {
+                    const uint32_t pr = xs[i];
+                    const float4 *a = S + (pr & 0xFFFFu), *b = S + (pr >> 16);
+                    const int rank = CV ? (int)xsr[i] : 0;
 #pragma unroll
-                for (int c = 0; c < KP_QPT; c++) {
-                    int q = q0 + c * KP_NT;
-                    if (q < nq) { ((float2 *)S)[q] = hv[c]; ((float2 *)T)[q] = ht[c]; }
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- phase E: wavefront over the tile's own levels ----
-        for (int ml = 0; ml < nml; ml++) {
-            const uint32_t lo = mlo[ml], hi = mlo[ml + 1];
-            for (uint32_t i = lo + tid; i < hi; i += KP_NT) {
-                const uint32_t pk = cl[i];
-                const uint32_t cell = (pk >> 16) & 0xFFFu;
-                float lv = INF;
-                uint32_t lr = 0xFFu;
-                int o1 = 0, o2 = 0;
-                for (int e = 0; e < nlow; e++) {
-                    const uint32_t lm = lowmeta[e];
-                    int d = (int)((pk >> (lm & 0xFFu)) & ((lm >> 8) & 0xFFu));
-                    int ns = lowns[e * 16 + d];
-                    const int *dl = lowd + e * 128 + d * 8;
-                    uint32_t rb = lm >> 16;
-                    for (int j = 0; j < ns; j++) {
-                        int w = dl[j];
-                        int a1 = (int)cell + (int)(short)(w & 0xFFFF), a2 = (int)cell + (w >> 16);
-                        float v = __fadd_rn(S[a1], S[a2]);
-                        if (v < lv) { lv = v; lr = rb + j; o1 = a1; o2 = a2; }
+                    for (int g = 0; g < NG; g++) {
+                        float4 xa = a[g * rp], xb = b[g * rp];
+                        float c0 = __fadd_rn(xa.x, xb.x), c1 = __fadd_rn(xa.y, xb.y);
+                        float c2 = __fadd_rn(xa.z, xb.z), c3 = __fadd_rn(xa.w, xb.w);
+                        if (!CV) {
+                            r.v[4 * g + 0] = fminf(r.v[4 * g + 0], c0);
+                            r.v[4 * g + 1] = fminf(r.v[4 * g + 1], c1);
+                            r.v[4 * g + 2] = fminf(r.v[4 * g + 2], c2);
+                            r.v[4 * g + 3] = fminf(r.v[4 * g + 3], c3);
+                        } else {
+                            // cross-row and streamed splits interleave in scan order: compare (value, rank)
+#define KP_CVX(c, cand)                                                                                          \
+    if ((cand) < r.v[c] || ((cand) == r.v[c] && rank < (r.rk[c] & ~KP_FETCH))) { r.v[c] = (cand); r.rk[c] = rank | KP_FETCH; }
+                            KP_CVX(4 * g + 0, c0) KP_CVX(4 * g + 1, c1) KP_CVX(4 * g + 2, c2) KP_CVX(4 * g + 3, c3)
+#undef KP_CVX
+                        }
                     }
                 }
-                const float hv = S[cell];
-                const double s = ((const double *)slot)[cell];
-                if (!CV) {
-                    if (hv < lv) { lv = hv; lr = R[cell]; }       // low positions scan first: they keep ties
-                    if (s < (double)lv) { lv = __double2float_rn(s); lr = 0xFFu; }
-                    S[cell] = lv;
-                    R[cell] = (uint8_t)lr;
+
+                // ---- register position: in-register splits + self-score, digit by digit ----
+                const bool leafrow = p.leaf_wave && row_level[srow] == 0;
+                // CV: fetch the held-out loss of a winner that came from memory (streamed or cross-row split)
+                auto fetch_test = [&](int d, int rank) -> float {
+                    const int inrow = ((d >> 2) * rp) * 4 + (d & 3);
+                    for (int i = xs_off[srow]; i < xs_off[srow + 1]; i++)
+                        if ((int)xsr[i] == rank) {
+                            const float *t0 = p.test + (size_t)tile * stride + inrow;
+                            return __fadd_rn(__ldcg(t0 + (xs[i] & 0xFFFFu) * 4), __ldcg(t0 + (xs[i] >> 16) * 4));
+                        }
+                    for (int s = 0; s < nhs; s++)
+                        if ((int)hsr[s] == rank)
+                            return __fadd_rn(__ldg(p.test + (size_t)hs1[s] * stride + inrow + srow * 4),
+                                             __ldg(p.test + (size_t)hs2[s] * stride + inrow + srow * 4));
+                    return 0.f;
+                };
+#define KP_FIN(D, BM)                                                                                            \
+    {                                                                                                            \
+        C M_ = Ops::template sum<BM>(r.m), U_ = Ops::template sum<BM>(r.u);                                      \
+        double s_, lp_ = 0.0, l1_ = 0.0, t_ = 0.0;                                                               \
+        const bool leaf_ = leafrow && (D) < NB;                                                                  \
+        if (!CV) {                                                                                               \
+            if (leaf_) s_ = (double)__double2float_rn(kp_leaf_score_nl(M_, U_, alpha, beta, penalty, logtab));   \
+            else s_ = kp_self_score_t<C>(M_, U_, alpha, beta, penalty, logtab, lp_, l1_);                        \
+            if (s_ < (double)r.v[D]) { r.v[D] = __double2float_rn(s_); r.flag |= 1u << (D); }                    \
+        } else {                                                                                                 \
+            C Mt_ = Ops::template sum<BM>(r.mt), Ut_ = Ops::template sum<BM>(r.ut);                              \
+            if (leaf_) {                                                                                         \
+                kp_leaf_cv_nl(M_, U_, Mt_, Ut_, alpha, beta, penalty, logtab, &s_, &t_);                         \
+                s_ = (double)__double2float_rn(s_);                                                              \
+            } else {                                                                                             \
+                s_ = kp_self_score_t<C>(M_, U_, alpha, beta, penalty, logtab, lp_, l1_);                         \
+                t_ = kp_test_ll((unsigned long long)Mt_, (unsigned long long)Ut_, lp_, l1_);                     \
+            }                                                                                                    \
+            if (s_ < (double)r.v[D]) { r.v[D] = __double2float_rn(s_); r.tv[D] = __double2float_rn(t_); }        \
+            else if (r.rk[D] & KP_FETCH) r.tv[D] = fetch_test(D, r.rk[D] & ~KP_FETCH);                           \
+        }                                                                                                        \
+    }
+#define KP_SP(D, A, B, J) Ops::template split<D, A, B, J>(r, rankbase);
+                if (R0 == 1) {
+                    KP_FIN(0, 1)
+                } else if (R0 == 3) {
+                    KP_FIN(0, 1) KP_FIN(1, 2)
+                    KP_SP(2, 0, 1, 0) KP_FIN(2, 3)
+                } else if (R0 == 7) {
+                    KP_FIN(0, 1) KP_FIN(1, 2) KP_FIN(2, 4)
+                    KP_SP(3, 0, 1, 0) KP_FIN(3, 3)
+                    KP_SP(4, 0, 2, 0) KP_FIN(4, 5)
+                    KP_SP(5, 1, 2, 0) KP_FIN(5, 6)
+                    KP_SP(6, 0, 5, 0) KP_SP(6, 1, 4, 1) KP_SP(6, 2, 3, 2) KP_FIN(6, 7)
                 } else {
-                    float tv;
-                    if (hv < lv) { lv = hv; tv = T[cell]; }
-                    else tv = __fadd_rn(T[o1], T[o2]);
-                    if (s < (double)lv) {
-                        lv = __double2float_rn(s);
-                        tv = ((const float *)(slot + (size_t)(WIDE ? 2 : 1) * stride))[2 * (size_t)cell];
-                    }
-                    S[cell] = lv;
-                    T[cell] = tv;
+                    KP_FIN(0, 1) KP_FIN(1, 2) KP_FIN(2, 4) KP_FIN(3, 8)
+                    KP_SP(4, 0, 2, 0) KP_FIN(4, 5)     // R = A|G
+                    KP_SP(5, 1, 3, 0) KP_FIN(5, 10)    // Y = C|T
+                    KP_SP(6, 2, 1, 0) KP_FIN(6, 6)     // S = G|C
+                    KP_SP(7, 0, 3, 0) KP_FIN(7, 9)     // W = A|T
+                    KP_SP(8, 2, 3, 0) KP_FIN(8, 12)    // K = G|T
+                    KP_SP(9, 0, 1, 0) KP_FIN(9, 3)     // M = A|C
+                    KP_SP(10, 1, 8, 0) KP_SP(10, 2, 5, 1) KP_SP(10, 3, 6, 2) KP_FIN(10, 14)   // B
+                    KP_SP(11, 0, 8, 0) KP_SP(11, 2, 7, 1) KP_SP(11, 3, 4, 2) KP_FIN(11, 13)   // D
+                    KP_SP(12, 0, 5, 0) KP_SP(12, 1, 7, 1) KP_SP(12, 3, 9, 2) KP_FIN(12, 11)   // H
+                    KP_SP(13, 0, 6, 0) KP_SP(13, 1, 4, 1) KP_SP(13, 2, 9, 2) KP_FIN(13, 7)    // V
+                    KP_SP(14, 6, 7, 0) KP_SP(14, 8, 9, 1) KP_SP(14, 4, 5, 2) KP_SP(14, 0, 10, 3)
+                    KP_SP(14, 1, 11, 4) KP_SP(14, 2, 12, 5) KP_SP(14, 3, 13, 6) KP_FIN(14, 15)  // N
                 }
+#undef KP_FIN
+#undef KP_SP
+                // ---- store the row ----
+#pragma unroll
+                for (int c = R0; c < NG * 4; c++) { r.v[c] = 0.f; if (CV) r.tv[c] = 0.f; }
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+                    float4 o = make_float4(r.v[4 * g], r.v[4 * g + 1], r.v[4 * g + 2], r.v[4 * g + 3]);
+                    S[g * rp + srow] = o;
+                    otile[g * rp + srow] = o;
+                    if (CV) {
+                        float4 ot = make_float4(r.tv[4 * g], r.tv[4 * g + 1], r.tv[4 * g + 2], r.tv[4 * g + 3]);
+                        ((float4 *)(p.test + (size_t)tile * stride))[g * rp + srow] = ot;
+                    }
+                }
+                if (!CV) p.flags[(size_t)tile * rp + srow] = (uint16_t)r.flag;
             }
-            __syncthreads();
+            __syncwarp();  // rows of this round (shared S, and for CV the global test rows) visible to the warp
         }
-
-        // ---- phase F: write the tile ----
-        if (!CV) {
-            const int nq = (int)((cells + 3) >> 2);
-            float4 *ob = (float4 *)(p.best + (size_t)tile * stride);
-            uint32_t *os = (uint32_t *)(p.split + (size_t)tile * stride);
-            for (int q = tid; q < nq; q += KP_NT) { ob[q] = ((const float4 *)S)[q]; os[q] = ((const uint32_t *)R)[q]; }
-        } else {
-            const int nq = (int)((cells + 1) >> 1);
-            float4 *ot = (float4 *)(p.tt + (size_t)tile * stride * 2);
-            for (int q = tid; q < nq; q += KP_NT) {
-                float2 a = ((const float2 *)S)[q], b = ((const float2 *)T)[q];
-                ot[q] = make_float4(a.x, b.x, a.y, b.y);
-            }
-        }
-        __syncthreads();
     }
 }
 
@@ -344,7 +383,7 @@ __global__ void kp_pack_kernel(const KpTables *tab, const uint8_t *gen_mask, int
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         unsigned long long code = codes[i];
-        unsigned long long kidx = 0, kw = 1;
+        unsigned long long kidx = 0;
         int e = 0;
         bool ok = true;
         for (int s = 0; s < k; s++) {
@@ -352,8 +391,7 @@ __global__ void kp_pack_kernel(const KpTables *tab, const uint8_t *gen_mask, int
             unsigned g = gen_mask[s];
             if (m == 0 || (m & (m - 1)) || !(m & g)) { ok = false; break; }
             if (g & (g - 1)) {  // multi-letter position: carries a digit
-                kidx += (unsigned long long)tb.mask_digit[e][m] * kw;
-                kw *= tb.nbase[e];
+                kidx += (unsigned long long)tb.mask_digit[e][m] * tb.kw[e];
                 e++;
             }
         }
@@ -373,22 +411,25 @@ __global__ void kp_expand_base_kernel(const KpTables *tab, unsigned long long nk
     const uint32_t tk = tb.tile_kmers;
     for (unsigned long long x = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; x < nkmer;
          x += (unsigned long long)gridDim.x * blockDim.x) {
-        unsigned long long kl = x % tk, kh = x / tk, tile = 0;
-        for (int e = tb.nlow; e < tb.npos; e++) {
-            tile += (kh % tb.nbase[e]) * tb.highw[e];
-            kh /= tb.nbase[e];
+        unsigned long long rest = x, tile = 0, kl = 0;
+        for (int e = 0; e < tb.npos; e++) {
+            unsigned long long b = rest % tb.nbase[e];
+            rest /= tb.nbase[e];
+            if (tb.is_low[e]) kl += b * tb.lkw[e];
+            else tile += b * tb.highw[e];  // single-nucleotide digit == base index
         }
         expM[tile * tk + kl] = kmerM[x];
         expU[tile * tk + kl] = kmerU[x];
     }
 }
 
-// pass over high position e: tiles whose digit at e is multi-letter and whose higher digits are single
-__global__ void kp_expand_pass_kernel(const KpTables *tab, int e, long long *expM, long long *expU)
+// pass over the hi-th high position: tiles whose digit there is multi-letter and whose later high digits are single
+__global__ void kp_expand_pass_kernel(const KpTables *tab, int hi, long long *expM, long long *expU)
 {
     const KpTables &tb = *tab;
     const uint32_t tk = tb.tile_kmers;
     const unsigned long long total = (unsigned long long)tb.ntiles * tk;
+    const int e = tb.highpos[hi];
     const uint32_t hw = tb.highw[e], rad = tb.radix[e], nb = tb.nbase[e];
     for (unsigned long long x = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; x < total;
          x += (unsigned long long)gridDim.x * blockDim.x) {
@@ -398,7 +439,8 @@ __global__ void kp_expand_pass_kernel(const KpTables *tab, int e, long long *exp
         if (d < nb) continue;
         rest /= rad;
         bool ok = true;
-        for (int f = e + 1; f < tb.npos; f++) {
+        for (int h = hi + 1; h < tb.nhigh; h++) {
+            int f = tb.highpos[h];
             if (rest % tb.radix[f] >= tb.nbase[f]) { ok = false; break; }
             rest /= tb.radix[f];
         }
@@ -417,18 +459,70 @@ __global__ void kp_expand_pass_kernel(const KpTables *tab, int e, long long *exp
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Locating a dense pattern number in the device layout, and re-deriving its split decision
+// ---------------------------------------------------------------------------------------------------
+struct KpLoc { unsigned long long tile; uint32_t srow, d0; };
+
+__device__ __forceinline__ KpLoc kp_locate_dev(const KpTables &tb, const uint16_t *srow_of_row, unsigned long long pat)
+{
+    KpLoc L;
+    L.tile = 0; L.d0 = 0;
+    uint32_t row = 0;
+    for (int e = 0; e < tb.npos; e++) {
+        uint32_t dig = (uint32_t)((pat / tb.extw[e]) % tb.radix[e]);
+        if (e == tb.estar) L.d0 = dig;
+        else if (tb.is_low[e]) row += dig * tb.roww[e];
+        else L.tile += (unsigned long long)dig * tb.highw[e];
+    }
+    L.srow = srow_of_row[row];
+    return L;
+}
+
+__device__ __forceinline__ float kp_best_at(const KpTables &tb, const uint16_t *srow_of_row, const float *best,
+                                            unsigned long long pat)
+{
+    KpLoc L = kp_locate_dev(tb, srow_of_row, pat);
+    return best[L.tile * tb.tile_stride + ((size_t)(L.d0 >> 2) * tb.rp + L.srow) * 4 + (L.d0 & 3)];
+}
+
+// The split the reference would have recorded for `pat` (w_numba.py:36-49, :62-64): 0xFF if the pattern is
+// kept whole, else position*8 + j of the first split in scan order whose float32 child sum is the minimum.
+__device__ uint8_t kp_split_code_dev(const KpTables &tb, const uint16_t *srow_of_row, const float *best,
+                                     const uint16_t *flags, unsigned long long pat, unsigned long long *c1_out,
+                                     unsigned long long *c2_out)
+{
+    KpLoc L = kp_locate_dev(tb, srow_of_row, pat);
+    if ((flags[L.tile * tb.rp + L.srow] >> L.d0) & 1u) return 0xFF;
+    float bv = __int_as_float(0x7f800000);
+    uint8_t code = 0xFF;
+    for (int e = 0; e < tb.npos; e++) {
+        unsigned long long w = tb.extw[e];
+        int d = (int)((pat / w) % tb.radix[e]);
+        uint32_t m = tb.digit_mask[e][d];
+        for (int j = 0; j < tb.ms_n[m]; j++) {
+            int c1 = tb.mask_digit[e][tb.ms_c1[m][j]], c2 = tb.mask_digit[e][tb.ms_c2[m][j]];
+            unsigned long long p1 = pat - (unsigned long long)(d - c1) * w, p2 = pat - (unsigned long long)(d - c2) * w;
+            float v = __fadd_rn(kp_best_at(tb, srow_of_row, best, p1), kp_best_at(tb, srow_of_row, best, p2));
+            if (v < bv) { bv = v; code = (uint8_t)(tb.pos_id[e] * 8 + j); *c1_out = p1; *c2_out = p2; }
+        }
+    }
+    return code;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // K5: backtrack.  Breadth-first expansion from the general pattern; each leaf carries its path key
 // (0 = c1 side, 1 = c2 side, most significant bit first), so sorting by key restores the reference's
 // depth-first, c1-first emission order.
 // ---------------------------------------------------------------------------------------------------
 struct KpBtNode { unsigned long long pat, key; };
 
-__global__ void __launch_bounds__(256) kp_backtrack_kernel(const KpTables *tab, const uint8_t *split,
-                                                           unsigned long long top, KpBtNode *fa, KpBtNode *fb,
-                                                           KpBtNode *leaves, unsigned long long cap,
+__global__ void __launch_bounds__(256) kp_backtrack_kernel(const KpTables *tab, const uint8_t *rowtab, const float *best,
+                                                           const uint16_t *flags, unsigned long long top, KpBtNode *fa,
+                                                           KpBtNode *fb, KpBtNode *leaves, unsigned long long cap,
                                                            unsigned long long *out_counts /* [0]=nleaves [1]=overflow */)
 {
     const KpTables &tb = *tab;
+    const uint16_t *srow_of_row = (const uint16_t *)(rowtab + tb.rt_srow_of_row);
     __shared__ unsigned long long s_ncur, s_nnext, s_nleaf;
     __shared__ int s_over;
     if (threadIdx.x == 0) { s_ncur = 1; s_nnext = 0; s_nleaf = 0; s_over = 0; fa[0].pat = top; fa[0].key = 0; }
@@ -439,25 +533,18 @@ __global__ void __launch_bounds__(256) kp_backtrack_kernel(const KpTables *tab, 
         if (ncur == 0) break;
         for (unsigned long long i = threadIdx.x; i < ncur; i += blockDim.x) {
             KpBtNode nd = cur[i];
-            unsigned long long tile = nd.pat / tb.tile_cells;
-            uint32_t cell = (uint32_t)(nd.pat % tb.tile_cells);
-            uint8_t code = split[tile * tb.tile_stride + cell];
+            unsigned long long p1 = 0, p2 = 0;
+            uint8_t code = kp_split_code_dev(tb, srow_of_row, best, flags, nd.pat, &p1, &p2);
             if (code == 0xFF) {
                 unsigned long long li = atomicAdd(&s_nleaf, 1ULL);
                 if (li < cap) leaves[li] = nd; else s_over = 1;
                 continue;
             }
-            int pos = code >> 3, j = code & 7, e = 0;
-            for (int f = 0; f < tb.npos; f++) if (tb.pos_id[f] == pos) e = f;
-            unsigned long long w = tb.extw[e];
-            int d = (int)((nd.pat / w) % tb.radix[e]);
-            uint32_t m = tb.digit_mask[e][d];
-            int c1 = tb.mask_digit[e][tb.ms_c1[m][j]], c2 = tb.mask_digit[e][tb.ms_c2[m][j]];
             unsigned long long ni = atomicAdd(&s_nnext, 2ULL);
             if (ni + 2 > cap) { s_over = 1; continue; }
-            nxt[ni].pat = nd.pat - (unsigned long long)(d - c1) * w;
+            nxt[ni].pat = p1;
             nxt[ni].key = nd.key;
-            nxt[ni + 1].pat = nd.pat - (unsigned long long)(d - c2) * w;
+            nxt[ni + 1].pat = p2;
             nxt[ni + 1].key = nd.key | (1ULL << (63 - depth));
         }
         __syncthreads();
@@ -486,6 +573,42 @@ __global__ void kp_backtrack_sort_kernel(const KpBtNode *leaves, const unsigned 
         __syncthreads();
     }
     if (i < n) out[rank] = leaves[i].pat;
+}
+
+// split codes of arbitrary patterns (test hook and output stage)
+__global__ void kp_split_codes_kernel(const KpTables *tab, const uint8_t *rowtab, const float *best, const uint16_t *flags,
+                                      const unsigned long long *pats, unsigned long long n, uint8_t *codes)
+{
+    const KpTables &tb = *tab;
+    const uint16_t *srow_of_row = (const uint16_t *)(rowtab + tb.rt_srow_of_row);
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long p1, p2;
+        codes[i] = kp_split_code_dev(tb, srow_of_row, best, flags, pats[i], &p1, &p2);
+    }
+}
+
+// gather table values of arbitrary patterns: out[i] = table[pattern i]  (also: unpacks whole tables for tests)
+__global__ void kp_gather_kernel(const KpTables *tab, const uint8_t *rowtab, const float *table,
+                                 const unsigned long long *pats, unsigned long long first, unsigned long long n, float *out)
+{
+    const KpTables &tb = *tab;
+    const uint16_t *srow_of_row = (const uint16_t *)(rowtab + tb.rt_srow_of_row);
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        out[i] = kp_best_at(tb, srow_of_row, table, pats ? pats[i] : first + i);
+}
+
+__global__ void kp_gather_flags_kernel(const KpTables *tab, const uint8_t *rowtab, const uint16_t *flags,
+                                       unsigned long long first, unsigned long long n, uint8_t *out)
+{
+    const KpTables &tb = *tab;
+    const uint16_t *srow_of_row = (const uint16_t *)(rowtab + tb.rt_srow_of_row);
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        KpLoc L = kp_locate_dev(tb, srow_of_row, first + i);
+        out[i] = (uint8_t)((flags[L.tile * tb.rp + L.srow] >> L.d0) & 1u);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -1,4 +1,4 @@
-// kp_plan.cpp — builds the index/split tables of one general pattern on the host.
+// kp_plan.cpp — builds the index/split/schedule tables of one general pattern on the host.
 //
 // Restates, as nucleotide-subset masks (A=1, C=2, G=4, T=8), the reference's letter tables:
 //   src/kmerpapa/pattern_utils.py:5-19 (`code`), :48-57 (`complements`), :86-100 (`perm_code`).
@@ -45,6 +45,12 @@ const Letter *find_letter(char c)
 
 int popc4(unsigned m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + ((m >> 3) & 1); }
 
+// The DP kernel hard-codes, per radix of the register position, which base digits each digit covers.
+// (digit-space structure; identical for every letter of the same size — checked below)
+const uint8_t kDigitBases3[3] = {1, 2, 3};
+const uint8_t kDigitBases7[7] = {1, 2, 4, 3, 5, 6, 7};
+const uint8_t kDigitBases15[15] = {1, 2, 4, 8, 5, 10, 6, 9, 12, 3, 14, 13, 11, 7, 15};
+
 }  // namespace
 
 int kp_build_host_plan(const char *gen_pat, KpHostPlan &P, std::string &err)
@@ -84,14 +90,24 @@ int kp_build_host_plan(const char *gen_pat, KpHostPlan &P, std::string &err)
         t.radix[e] = (uint8_t)radix;
         t.nbase[e] = (uint8_t)strlen(g->bases);
         t.extw[e] = npat;
+        if (nkmer >= (1ull << 31)) { err = "too many k-mers"; return 5; }
+        t.kw[e] = (uint32_t)nkmer;
         for (int d = 0; d < radix; d++) {
             uint8_t m = find_letter(g->digits[d])->mask;
             t.digit_mask[e][d] = m;
             t.mask_digit[e][m] = (uint8_t)d;
         }
-        // singleton digits must enumerate the bases in `code` order (k-mer index == digit for k-mers)
+        // single-nucleotide digits must enumerate the bases in `code` order (k-mer base index == digit)
         for (int b = 0; b < t.nbase[e]; b++)
             if (g->digits[b] != g->bases[b]) { err = "internal: base/digit order mismatch"; return 4; }
+        // digit-space structure the kernel hard-codes
+        const uint8_t *want = radix == 3 ? kDigitBases3 : radix == 7 ? kDigitBases7 : kDigitBases15;
+        for (int d = 0; d < radix; d++) {
+            unsigned got = 0;
+            for (int b = 0; b < 4; b++)
+                if ((t.digit_mask[e][d] >> b) & 1) got |= 1u << t.mask_digit[e][1 << b];
+            if (got != want[d]) { err = "internal: digit structure mismatch"; return 4; }
+        }
         if (npat > (UINT64_MAX / 16)) { err = "pattern table too large"; return 5; }
         npat *= (uint64_t)radix;
         nkmer *= (uint64_t)t.nbase[e];
@@ -102,97 +118,181 @@ int kp_build_host_plan(const char *gen_pat, KpHostPlan &P, std::string &err)
     t.npos = npos;
     t.total_level = (uint32_t)total_level;
 
-    // low positions: longest prefix whose cells fit a tile and whose digit fields fit 16 bits
-    int nlow = 0, bits = 0;
-    uint32_t cells = 1, tk = 1;
-    while (nlow < npos && nlow < KP_MAXLOW) {
-        int r = t.radix[nlow];
-        int b = r <= 3 ? 2 : (r <= 7 ? 3 : 4);
-        if ((uint64_t)cells * r > KP_MAX_TILE || bits + b > 16) break;
-        t.shift[nlow] = (uint8_t)bits;
-        t.fmask[nlow] = (uint8_t)((1 << b) - 1);
-        t.loww[nlow] = cells;
-        t.lowkw[nlow] = tk;
-        bits += b;
-        cells *= r;
-        tk *= t.nbase[nlow];
-        nlow++;
-    }
-    t.nlow = nlow;
-    t.nhigh = npos - nlow;
-    t.tile_cells = cells;
-    t.tile_stride = (cells + 31u) & ~31u;
-    t.tile_kmers = tk;
-    uint64_t ntiles = npat / cells;
-    if (ntiles >= (1ull << 31)) { err = "too many tiles"; return 6; }
-    t.ntiles = (uint32_t)ntiles;
-    {
-        uint32_t hw = 1, hkw = 1;
-        for (int e = nlow; e < npos; e++) {
+    // ---- choose the low positions: largest radices first (ties: lowest position), product <= KP_MAX_TILE ----
+    std::vector<int> byradix(npos);
+    for (int e = 0; e < npos; e++) byradix[e] = e;
+    std::stable_sort(byradix.begin(), byradix.end(), [&](int a, int b) { return t.radix[a] > t.radix[b]; });
+    uint32_t cells = 1;
+    for (int e : byradix)
+        if ((uint64_t)cells * t.radix[e] <= KP_MAX_TILE) { t.is_low[e] = 1; cells *= t.radix[e]; }
+    t.estar = npos > 0 ? byradix[0] : -1;
+    t.r0 = npos > 0 ? t.radix[t.estar] : 1;
+    t.nb0 = npos > 0 ? t.nbase[t.estar] : 1;
+    t.ng = (t.r0 + 3) / 4;
+    std::vector<int> rowpos;  // low positions other than estar, ascending
+    uint32_t roww = 1, lkw = (uint32_t)t.nb0, hw = 1, tk = (uint32_t)t.nb0;
+    if (t.estar >= 0) t.lkw[t.estar] = 1;
+    for (int e = 0; e < npos; e++) {
+        if (t.is_low[e]) {
+            t.nlow++;
+            if (e == t.estar) continue;
+            rowpos.push_back(e);
+            t.roww[e] = roww;
+            t.lkw[e] = lkw;
+            roww *= t.radix[e];
+            lkw *= t.nbase[e];
+            tk *= t.nbase[e];
+        } else {
+            t.highpos[t.nhigh++] = (uint8_t)e;
             t.highw[e] = hw;
-            t.highkw[e] = hkw;
+            if ((uint64_t)hw * t.radix[e] >= (1ull << 31)) { err = "too many tiles"; return 6; }
             hw *= t.radix[e];
-            hkw *= t.nbase[e];
         }
     }
+    t.nrows = (int32_t)roww;
+    t.rp = (t.nrows + 1) & ~1;
+    t.tile_cells = cells;
+    t.tile_stride = (uint32_t)(t.ng * t.rp * 4);
+    t.tile_kmers = tk;
+    t.ntiles = hw;
+    const uint64_t ntiles = hw;
 
-    // per low position split offsets
-    for (int e = 0; e < nlow; e++) {
-        for (int d = 0; d < t.radix[e]; d++) {
-            uint8_t m = t.digit_mask[e][d];
-            int ns = t.ms_n[m];
-            t.low_ns[e][d] = (uint8_t)ns;
-            for (int j = 0; j < ns; j++) {
+    // ---- rows of a tile ----
+    const int nrows = t.nrows;
+    std::vector<std::vector<std::pair<int, int>>> xsplit(nrows);  // (c1 row, c2 row) in scan order
+    std::vector<std::vector<uint8_t>> xrank(nrows);               // scan rank (string position * 8 + j) of each
+    std::vector<std::vector<uint16_t>> bases(nrows);              // base rows covered
+    std::vector<int> level(nrows, 0);
+    for (int r = 0; r < nrows; r++) {
+        int dig[KP_MAXPOS] = {0};
+        uint32_t x = (uint32_t)r;
+        for (int e : rowpos) { dig[e] = (int)(x % t.radix[e]); x /= t.radix[e]; }
+        std::vector<uint32_t> acc(1, 0);
+        for (int e : rowpos) {
+            uint8_t m = t.digit_mask[e][dig[e]];
+            level[r] += popc4(m) - 1;
+            for (int j = 0; j < t.ms_n[m]; j++) {
                 int c1 = t.mask_digit[e][t.ms_c1[m][j]], c2 = t.mask_digit[e][t.ms_c2[m][j]];
-                if (c1 == 0xFF || c2 == 0xFF || c1 >= d || c2 >= d) { err = "internal: split table"; return 7; }
-                t.low_d1[e][d][j] = (int16_t)((c1 - d) * (int)t.loww[e]);
-                t.low_d2[e][d][j] = (int16_t)((c2 - d) * (int)t.loww[e]);
+                if (c1 == 0xFF || c2 == 0xFF || c1 >= dig[e] || c2 >= dig[e]) { err = "internal: split table"; return 7; }
+                xsplit[r].push_back({r - (dig[e] - c1) * (int)t.roww[e], r - (dig[e] - c2) * (int)t.roww[e]});
+                xrank[r].push_back((uint8_t)(t.pos_id[e] * 8 + j));
             }
+            std::vector<uint32_t> nxt;
+            for (uint32_t a : acc)
+                for (int b = 0; b < 4; b++)
+                    if ((m >> b) & 1) nxt.push_back(a + (uint32_t)t.mask_digit[e][1 << b] * (t.lkw[e] / (uint32_t)t.nb0));
+            acc.swap(nxt);
         }
+        std::sort(acc.begin(), acc.end());
+        for (uint32_t a : acc) bases[r].push_back((uint16_t)a);
     }
+    // list scheduling into rounds of <= 32 rows whose children all sit in earlier rounds
+    std::vector<int> height(nrows, 0), pending(nrows, 0);
+    std::vector<std::vector<int>> parents(nrows);
+    for (int r = 0; r < nrows; r++) {
+        std::vector<int> ch;
+        for (auto &pr : xsplit[r]) { ch.push_back(pr.first); ch.push_back(pr.second); }
+        std::sort(ch.begin(), ch.end());
+        ch.erase(std::unique(ch.begin(), ch.end()), ch.end());
+        pending[r] = (int)ch.size();
+        for (int c : ch) parents[c].push_back(r);
+    }
+    for (int r = nrows - 1; r >= 0; r--)  // parents have larger row numbers
+        for (int q : parents[r]) height[r] = std::max(height[r], height[q] + 1);
+    std::vector<int> ready, order;
+    std::vector<uint16_t> round_start(1, 0);
+    for (int r = 0; r < nrows; r++)
+        if (pending[r] == 0) ready.push_back(r);
+    while ((int)order.size() < nrows) {
+        if (ready.empty()) { err = "internal: row schedule"; return 8; }
+        std::sort(ready.begin(), ready.end(), [&](int a, int b) {
+            if (height[a] != height[b]) return height[a] > height[b];
+            if (xsplit[a].size() != xsplit[b].size()) return xsplit[a].size() > xsplit[b].size();
+            return a < b;
+        });
+        int take = std::min<int>(32, (int)ready.size());
+        std::vector<int> now(ready.begin(), ready.begin() + take);
+        ready.erase(ready.begin(), ready.begin() + take);
+        std::sort(now.begin(), now.end(), [&](int a, int b) {  // similar cost next to each other
+            if (xsplit[a].size() != xsplit[b].size()) return xsplit[a].size() < xsplit[b].size();
+            return a < b;
+        });
+        for (int r : now) order.push_back(r);
+        round_start.push_back((uint16_t)order.size());
+        for (int r : now)
+            for (int q : parents[r])
+                if (--pending[q] == 0) ready.push_back(q);
+    }
+    t.nrounds = (int32_t)round_start.size() - 1;
+    P.row_of_srow.assign(order.begin(), order.end());
+    P.srow_of_row.assign(nrows, 0);
+    for (int s = 0; s < nrows; s++) P.srow_of_row[order[s]] = (uint16_t)s;
 
-    // cells sorted by mini-level, then by the per-position subset sizes (keeps warps uniform), then id
-    struct CellKey { uint32_t ml, sig, cell, packed; };
-    std::vector<CellKey> keys(cells);
-    int nml = 0;
-    for (uint32_t c = 0; c < cells; c++) {
-        uint32_t x = c, ml = 0, sig = 0, packed = 0, hns1 = 0;
-        for (int e = 0; e < nlow; e++) {
-            uint32_t d = x % t.radix[e];
-            x /= t.radix[e];
-            int sz = popc4(t.digit_mask[e][d]);
-            ml += (uint32_t)(sz - 1);
-            sig = sig * 4 + (uint32_t)(sz - 1);
-            packed |= d << t.shift[e];
-            if (sz > 1) hns1 = (uint32_t)e + 1;  // highest multi-letter low position, +1 (0: a k-mer cell)
+    // ---- blob ----
+    {
+        std::vector<uint8_t> &B = P.rowtab;
+        B.clear();
+        auto align = [&](size_t a) { while (B.size() % a) B.push_back(0); };
+        auto put16 = [&](uint32_t v) { B.push_back((uint8_t)(v & 0xFF)); B.push_back((uint8_t)((v >> 8) & 0xFF)); };
+        auto put32 = [&](uint32_t v) { for (int i = 0; i < 4; i++) B.push_back((uint8_t)(v >> (8 * i))); };
+        t.rt_round_start = (uint32_t)B.size();
+        for (uint16_t v : round_start) put16(v);
+        align(4);
+        t.rt_row_level = (uint32_t)B.size();
+        for (int s = 0; s < nrows; s++) B.push_back((uint8_t)level[order[s]]);
+        align(4);
+        t.rt_xs_off = (uint32_t)B.size();
+        {
+            uint32_t o = 0;
+            for (int s = 0; s < nrows; s++) { put16(o); o += (uint32_t)xsplit[order[s]].size(); }
+            put16(o);
+            if (o > 65535) { err = "internal: split list too long"; return 8; }
         }
-        packed |= hns1 << 28;
-        keys[c] = {ml, sig, c, packed};
-        nml = std::max(nml, (int)ml + 1);
+        align(4);
+        t.rt_xs = (uint32_t)B.size();
+        for (int s = 0; s < nrows; s++)
+            for (auto &pr : xsplit[order[s]])
+                put32((uint32_t)P.srow_of_row[pr.first] | ((uint32_t)P.srow_of_row[pr.second] << 16));
+        align(4);
+        t.rt_xs_rank = (uint32_t)B.size();
+        for (int s = 0; s < nrows; s++)
+            for (uint8_t rk : xrank[order[s]]) B.push_back(rk);
+        align(4);
+        t.rt_bs_off = (uint32_t)B.size();
+        {
+            uint32_t o = 0;
+            for (int s = 0; s < nrows; s++) { put16(o); o += (uint32_t)bases[order[s]].size(); }
+            put16(o);
+            if (o > 65535) { err = "internal: base list too long"; return 8; }
+        }
+        align(4);
+        t.rt_bs = (uint32_t)B.size();
+        for (int s = 0; s < nrows; s++)
+            for (uint16_t b : bases[order[s]]) put16(b);
+        align(4);
+        t.rt_srow_of_row = (uint32_t)B.size();
+        for (int r = 0; r < nrows; r++) put16(P.srow_of_row[r]);
+        align(16);
+        t.rt_bytes = (uint32_t)B.size();
     }
-    if (nml > KP_MAXML) { err = "internal: too many mini-levels"; return 8; }
-    std::sort(keys.begin(), keys.end(), [](const CellKey &a, const CellKey &b) {
-        if (a.ml != b.ml) return a.ml < b.ml;
-        if (a.sig != b.sig) return a.sig < b.sig;
-        return a.cell < b.cell;
-    });
-    t.nml = nml;
-    P.cell_list.resize(cells);
-    for (uint32_t i = 0; i < cells; i++) {
-        P.cell_list[i] = (keys[i].cell << 16) | keys[i].packed;  // [31:28] hns1, [27:16] cell, [15:0] digits
-        t.ml_off[keys[i].ml + 1]++;
-    }
-    for (int l = 0; l < nml; l++) t.ml_off[l + 1] += t.ml_off[l];
+    for (int cv = 0; cv < 2; cv++)
+        for (int wide = 0; wide < 2; wide++) {
+            size_t b = (size_t)t.ng * t.rp * 16;                 // S rows
+            b += (size_t)tk * (cv ? 2 : 1) * (wide ? 16 : 8);     // base counts
+            b += 2 * KP_MAXHS * 4 + KP_MAXHS + 16;                // high split list (two tiles, rank) + count
+            t.warp_smem_bytes[cv][wide] = (uint32_t)((b + 15) & ~(size_t)15);
+        }
 
-    // tiles sorted by high level
+    // ---- tiles sorted by high level ----
     int nhl = 1;
-    for (int e = nlow; e < npos; e++) nhl += t.nbase[e] - 1;
+    for (int i = 0; i < t.nhigh; i++) nhl += t.nbase[t.highpos[i]] - 1;
     std::vector<uint8_t> tl(ntiles);
     P.hl_off.assign((size_t)nhl + 1, 0);
     for (uint64_t tile = 0; tile < ntiles; tile++) {
         uint64_t x = tile;
         int l = 0;
-        for (int e = nlow; e < npos; e++) {
+        for (int i = 0; i < t.nhigh; i++) {
+            int e = t.highpos[i];
             l += popc4(t.digit_mask[e][x % t.radix[e]]) - 1;
             x /= t.radix[e];
         }
@@ -206,6 +306,22 @@ int kp_build_host_plan(const char *gen_pat, KpHostPlan &P, std::string &err)
         for (uint64_t tile = 0; tile < ntiles; tile++) P.tile_order[cur[tl[tile]]++] = (uint32_t)tile;
     }
     return 0;
+}
+
+void kp_locate(const KpHostPlan &P, uint64_t pat, uint64_t *tile, uint32_t *srow, uint32_t *d0)
+{
+    const KpTables &t = P.t;
+    uint64_t tl = 0;
+    uint32_t row = 0, d = 0;
+    for (int e = 0; e < t.npos; e++) {
+        uint32_t dig = (uint32_t)((pat / t.extw[e]) % t.radix[e]);
+        if (e == t.estar) d = dig;
+        else if (t.is_low[e]) row += dig * t.roww[e];
+        else tl += (uint64_t)dig * t.highw[e];
+    }
+    *tile = tl;
+    *srow = P.srow_of_row[row];
+    *d0 = d;
 }
 
 void kp_num2masks(const KpHostPlan &P, uint64_t num, uint8_t *masks_out)

@@ -12,7 +12,8 @@ struct KpHostPlan {
     int k = 0;
     uint64_t npat = 0, nkmer = 0;
     KpTables t;                        // uploaded verbatim
-    std::vector<uint32_t> cell_list;   // per cell, sorted by mini-level: (cell << 16) | packed digits
+    std::vector<uint8_t> rowtab;       // row tables blob (offsets in t.rt_*)
+    std::vector<uint16_t> srow_of_row, row_of_srow;  // natural row <-> schedule position
     std::vector<uint32_t> tile_order;  // tile ids sorted by (high level, tile id)
     std::vector<uint64_t> hl_off;      // offsets of the high levels in tile_order (size nhl + 1)
     uint8_t gen_mask[KP_MAXK];         // nucleotide subset of every string position (fixed ones too)
@@ -21,6 +22,9 @@ struct KpHostPlan {
 
 // Returns 0 on success; on failure fills err.
 int kp_build_host_plan(const char *gen_pat, KpHostPlan &P, std::string &err);
+
+// dense pattern number -> (tile, row in schedule order, digit of the register position)
+void kp_locate(const KpHostPlan &P, uint64_t pat, uint64_t *tile, uint32_t *srow, uint32_t *d0);
 
 // dense pattern number -> IUPAC string / nucleotide masks (host utility, mirrors num2pattern)
 void kp_num2masks(const KpHostPlan &P, uint64_t num, uint8_t *masks_out);

@@ -5,37 +5,45 @@
 //   :48-57   two-way splits (c1,c2) of a letter in scan order (`complements`)
 //   :86-100  digit order of the sub-letters of a general letter (`perm_code`)
 //   :237-257 dense pattern number = sum digit_i * w_i, position 0 least significant
+//
+// Geometry.  "Effective" positions are the multi-letter positions of the general pattern (fixed letters
+// carry no digit), numbered in string order.  A subset of them (largest radices first, product of
+// radices <= KP_MAX_TILE) is kept on chip: the LOW positions.  One of the low positions, `estar` (the
+// one with the largest radix r0), is the register dimension of the DP kernel; the other low positions
+// enumerate the `nrows` rows of a tile; the HIGH positions enumerate the tiles.
+//
+// Device layout of a float table: tile t, row in schedule order ("srow"), digit d of position estar at
+//   t * tile_stride + ((d >> 2) * rp + srow) * 4 + (d & 3)          (tile_stride = ng * rp * 4 floats)
+// i.e. each row is ng float4 groups and the 32 lanes of a warp touch consecutive rows (coalesced).
 #pragma once
 #include <stdint.h>
 
 #define KP_MAXK 32        // pattern length
-#define KP_MAXPOS 16      // positions with more than one letter (the others carry no digit)
-#define KP_MAXLOW 8       // positions kept inside a tile
-#define KP_MAXML 25       // mini-levels inside a tile (3 per low position + 1)
+#define KP_MAXPOS 16      // positions with more than one letter
 #define KP_MAX_TILE 4096  // cells per tile upper bound
 #define KP_MAXHS (KP_MAXPOS * 7)
 
-// Everything a kernel needs to know about one general pattern.  Lives in device global memory;
-// CTAs copy the hot parts to shared memory once.
 struct KpTables {
-    int32_t npos;    // effective (multi-letter) positions, ascending string position
-    int32_t nlow;    // the first nlow of them live inside a tile
-    int32_t nhigh;   // npos - nlow
-    int32_t nml;     // mini-levels inside a tile
+    int32_t npos;             // effective positions
+    int32_t nlow, nhigh;      // low (on-chip) and high (tile) positions
+    int32_t estar;            // effective index of the register position (-1: the pattern has no free position)
+    int32_t r0, nb0, ng;      // its radix / number of bases / float4 groups per row (1,1,1 when estar < 0)
+    int32_t nrows, rp;        // rows per tile, row pitch (nrows rounded up to even)
+    int32_t nrounds;          // schedule rounds (<= 32 rows each)
     uint32_t tile_cells, tile_stride, tile_kmers;
     uint32_t ntiles;
     uint32_t total_level;
 
-    uint8_t pos_id[KP_MAXPOS];   // string position (rank code = pos_id * 8 + split index)
-    uint8_t radix[KP_MAXPOS];    // 3, 7 or 15
-    uint8_t nbase[KP_MAXPOS];    // 2, 3 or 4
-    uint8_t shift[KP_MAXLOW];    // bit field of the digit inside a packed cell word
-    uint8_t fmask[KP_MAXLOW];
-    uint32_t loww[KP_MAXLOW];    // cell weight of a low position
-    uint32_t lowkw[KP_MAXLOW];   // low k-mer weight of a low position
-    uint32_t highw[KP_MAXPOS];   // tile weight of a high position (index npos-relative: [nlow..npos))
-    uint32_t highkw[KP_MAXPOS];  // high k-mer weight of a high position
-    uint64_t extw[KP_MAXPOS];    // dense pattern-number weight
+    uint8_t pos_id[KP_MAXPOS];    // string position of an effective position
+    uint8_t radix[KP_MAXPOS];     // 3, 7 or 15
+    uint8_t nbase[KP_MAXPOS];     // 2, 3 or 4
+    uint8_t is_low[KP_MAXPOS];
+    uint8_t highpos[KP_MAXPOS];   // effective indices of the high positions, ascending
+    uint32_t roww[KP_MAXPOS];     // row weight (low positions other than estar)
+    uint32_t highw[KP_MAXPOS];    // tile weight (high positions)
+    uint32_t kw[KP_MAXPOS];       // k-mer index weight (all effective positions, position 0 fastest)
+    uint32_t lkw[KP_MAXPOS];      // weight inside the tile's low k-mer index (estar fastest) for low positions
+    uint64_t extw[KP_MAXPOS];     // dense pattern-number weight
 
     uint8_t digit_mask[KP_MAXPOS][16];  // digit -> nucleotide subset (A=1,C=2,G=4,T=8)
     uint8_t mask_digit[KP_MAXPOS][16];  // subset -> digit (0xFF if not a sub-letter)
@@ -43,9 +51,16 @@ struct KpTables {
     uint8_t ms_n[16];       // number of two-way splits
     uint8_t ms_c1[16][7];   // c1 subset of split j
     uint8_t ms_c2[16][7];
-    // per low position, by digit: splits as negative cell offsets (c1 in .x, c2 in .y)
-    uint8_t low_ns[KP_MAXLOW][16];
-    int16_t low_d1[KP_MAXLOW][16][8];
-    int16_t low_d2[KP_MAXLOW][16][8];
-    uint32_t ml_off[KP_MAXML + 2];  // mini-level offsets into the cell list
+
+    // row tables blob (device global; CTAs copy it to shared memory): byte offsets into the blob
+    uint32_t rt_bytes;
+    uint32_t rt_round_start;  // u16 [nrounds + 1]   first srow of each round
+    uint32_t rt_row_level;    // u8  [nrows]         by srow; 0 = every row digit is a single nucleotide
+    uint32_t rt_xs_off;       // u16 [nrows + 1]     by srow; cross-row splits (CSR)
+    uint32_t rt_xs;           // u32 [...]           srow of c1 | srow of c2 << 16, scan order
+    uint32_t rt_xs_rank;      // u8  [...]           scan rank of each cross-row split (string position * 8 + j)
+    uint32_t rt_bs_off;       // u16 [nrows + 1]     by srow; base rows covered by the row (CSR)
+    uint32_t rt_bs;           // u16 [...]           base-row index (low k-mer index / nb0)
+    uint32_t rt_srow_of_row;  // u16 [nrows]         natural row -> srow
+    uint32_t warp_smem_bytes[2][2];  // per-warp shared memory of the DP kernel [cv][wide]
 };

@@ -106,28 +106,28 @@ class PartitionPlan:
 
     # -- K3+K4: single DP ------------------------------------------------------------------------
     def dp_single(self, eM, eU, max_count, alpha, beta, penalty):
+        """Returns (best, kept): float32 loss table and the uint16 kept-whole bit masks (device layout)."""
         torch = _torch()
-        n = int(self.info.table_elems)
-        best = self._buffer("best", n, torch.float32)
-        split = self._buffer("split", n, torch.uint8)
+        best = self._buffer("best", int(self.info.table_elems), torch.float32)
+        kept = self._buffer("kept", int(self.info.kept_elems), torch.int16)
         check(self.lib.kp_dp_single(self.handle, eM.data_ptr(), eU.data_ptr(), int(max_count), float(alpha), float(beta),
-                                    float(penalty), best.data_ptr(), split.data_ptr(), self._stream()), "kp_dp_single")
-        return best, split
+                                    float(penalty), best.data_ptr(), kept.data_ptr(), self._stream()), "kp_dp_single")
+        return best, kept
 
-    def top_score(self, best):
-        """np.float32 loss of the general pattern (device -> host read of one element)."""
-        idx = (int(self.info.ntiles) - 1) * int(self.info.tile_stride) + int(self.info.tile_cells) - 1
-        return np.float32(best[idx].item())
+    def top_score(self, table):
+        """np.float32 value of the general pattern in a device table."""
+        return self.gather(table, self.npat - 1, 1)[0]
 
     # -- K5: backtrack ---------------------------------------------------------------------------
-    def backtrack(self, split, cap=65536):
+    def backtrack(self, best, kept, cap=65536):
+        """Dense pattern numbers of the optimal partition in the reference's emission order."""
         torch = _torch()
         while True:
             ws = self._buffer("btws", int(self.lib.kp_backtrack_ws_bytes(cap)), torch.uint8)
             out = np.empty(cap, dtype=np.uint64)
             n = ctypes.c_uint64(0)
-            rc = self.lib.kp_backtrack(self.handle, split.data_ptr(), ws.data_ptr(), cap, out.ctypes.data, ctypes.byref(n),
-                                       self._stream())
+            rc = self.lib.kp_backtrack(self.handle, best.data_ptr(), kept.data_ptr(), ws.data_ptr(), cap, out.ctypes.data,
+                                       ctypes.byref(n), self._stream())
             if rc == 0:
                 return out[: n.value].copy()
             msg = self.lib.kp_last_error().decode()
@@ -136,19 +136,29 @@ class PartitionPlan:
                 continue
             raise KpError("kp_backtrack: " + msg)
 
+    def split_codes(self, best, kept, patnums):
+        """The reference's backtrack pointer as position*8+split codes (0xFF: kept whole)."""
+        patnums = np.ascontiguousarray(patnums, dtype=np.uint64)
+        out = np.empty(patnums.size, dtype=np.uint8)
+        check(self.lib.kp_split_codes(self.handle, best.data_ptr(), kept.data_ptr(), patnums.ctypes.data, patnums.size,
+                                      out.ctypes.data, self._stream()), "kp_split_codes")
+        return out
+
     # -- CV job ----------------------------------------------------------------------------------
     def cv_job(self, eMtot, eUtot, eMte, eUte, max_count, alpha, beta, penalty, read_top=True):
-        """One fold x alpha x penalty.  Returns (np.float32 train, np.float32 test) of the general pattern."""
+        """One fold x alpha x penalty.  Returns (np.float32 train, np.float32 test) of the general pattern,
+        or the (train, test) device tables when read_top is False."""
         torch = _torch()
         n = int(self.info.table_elems)
-        tt = self._buffer("tt", 2 * n, torch.float32)
+        train = self._buffer("cvtrain", n, torch.float32)
+        test = self._buffer("cvtest", n, torch.float32)
         top = (ctypes.c_float * 2)()
         check(self.lib.kp_dp_cv_job(self.handle, eMtot.data_ptr(), eUtot.data_ptr(), eMte.data_ptr(), eUte.data_ptr(),
-                                    int(max_count), float(alpha), float(beta), float(penalty), tt.data_ptr(),
-                                    ctypes.cast(top, ctypes.c_void_p) if read_top else None, self._stream()),
-              "kp_dp_cv_job")
+                                    int(max_count), float(alpha), float(beta), float(penalty), train.data_ptr(),
+                                    test.data_ptr(), ctypes.cast(top, ctypes.c_void_p) if read_top else None,
+                                    self._stream()), "kp_dp_cv_job")
         if not read_top:
-            return tt
+            return train, test
         return np.float32(top[0]), np.float32(top[1])
 
     # -- output stage ----------------------------------------------------------------------------
@@ -160,12 +170,21 @@ class PartitionPlan:
                                          M.ctypes.data, U.ctypes.data, self._stream()), "kp_pattern_counts")
         return M, U
 
-    # -- test/debug views ------------------------------------------------------------------------
-    def unpad(self, table, width=1):
-        """Tile-padded device table -> dense host array in the reference's pattern numbering."""
-        nt, st, tc = int(self.info.ntiles), int(self.info.tile_stride), int(self.info.tile_cells)
-        v = table[: nt * st * width].view(nt, st, width)[:, :tc, :]
-        return v.reshape(nt * tc, width).cpu().numpy()
+    # -- dense views (tests, exports) ------------------------------------------------------------
+    def gather(self, table, first=0, n=None):
+        """float32 values of patterns first..first+n-1 (dense numbering) from a device table."""
+        n = self.npat - first if n is None else n
+        out = np.empty(n, dtype=np.float32)
+        check(self.lib.kp_gather_table(self.handle, table.data_ptr(), int(first), int(n), out.ctypes.data, self._stream()),
+              "kp_gather_table")
+        return out
+
+    def gather_kept(self, kept, first=0, n=None):
+        n = self.npat - first if n is None else n
+        out = np.empty(n, dtype=np.uint8)
+        check(self.lib.kp_gather_kept(self.handle, kept.data_ptr(), int(first), int(n), out.ctypes.data, self._stream()),
+              "kp_gather_kept")
+        return out
 
 
 def get_plan(gen_pat, device=None):

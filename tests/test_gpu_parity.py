@@ -37,8 +37,10 @@ def _run_single(eng, gen_pat, M, U, alpha, beta, penalty, max_count=None):
     kM, kU = plan.pack_counts(_codes(gen_pat), M, U)
     eM, eU = plan.expand(kM, kU)
     mc = int(np.sum(M, dtype=np.uint64) + np.sum(U, dtype=np.uint64)) if max_count is None else max_count
-    best, split = plan.dp_single(eM, eU, mc, alpha, beta, penalty)
-    return plan, plan.unpad(best)[:, 0], plan.unpad(split)[:, 0], plan.backtrack(split)
+    best, kept = plan.dp_single(eM, eU, mc, alpha, beta, penalty)
+    split = plan.split_codes(best, kept, np.arange(plan.npat, dtype=np.uint64))   # the reference's backtrack pointer, as a code
+    assert np.array_equal(plan.gather_kept(kept) == 1, split == 0xFF)
+    return plan, plan.gather(best), split, plan.backtrack(best, kept)
 
 
 def test_device_log_is_glibc_log(eng, oracle):
@@ -138,25 +140,29 @@ def test_cv_jobs_against_reference_tables(eng, oracle, path):
                 kMf, kUf = plan.upload_kmer_tables(Mf[:, f], Uf[:, f], name="t_fold")
                 fold = plan.expand(kMf, kUf, name="t_fold_e")
                 for wide_mc in (mc, 1 << 40):
-                    tt = plan.cv_job(tot[0], tot[1], fold[0], fold[1], wide_mc, alpha, betas[f], pen, read_top=False)
-                    tab = plan.unpad(tt, width=2)
-                    assert np.array_equal(_bits(tab[:, 0]), _bits(g["train_tables"][gi][:, f]))
+                    train, test = plan.cv_job(tot[0], tot[1], fold[0], fold[1], wide_mc, alpha, betas[f], pen, read_top=False)
+                    tr, te = plan.gather(train), plan.gather(test)
+                    assert np.array_equal(_bits(tr), _bits(g["train_tables"][gi][:, f]))
                     if gi == len(alphas) * len(pens) - 1:
-                        assert np.array_equal(_bits(tab[:, 1]), _bits(g["last_test_table"][:, f]))
+                        assert np.array_equal(_bits(te), _bits(g["last_test_table"][:, f]))
                     else:
-                        _, te = oracle.cv_job(gp, Mtot, Utot, Mf[:, f], Uf[:, f], alpha, betas[f], pen)
-                        assert np.array_equal(_bits(tab[:, 1]), _bits(te))
+                        _, ote = oracle.cv_job(gp, Mtot, Utot, Mf[:, f], Uf[:, f], alpha, betas[f], pen)
+                        assert np.array_equal(_bits(te), _bits(ote))
+                    top = plan.cv_job(tot[0], tot[1], fold[0], fold[1], wide_mc, alpha, betas[f], pen)
+                    assert top[0].tobytes() == tr[-1].tobytes() and top[1].tobytes() == te[-1].tobytes()
             gi += 1
 
 
 @pytest.mark.parametrize("gen_pat,seed", [("NNNNN", 1), ("NNNMNN", 2), ("RYNNANNKM", 3), ("VNNNH", 4), ("NNNNNN", 5),
-                                          ("SWNNBNA", 6), ("MMMMMMMMMM", 7)])
+                                          ("SWNNBNA", 6), ("MMMMMMMMMM", 7), ("RYNNNANRY", 8), ("BBDHVVB", 9),
+                                          ("KNSNWNMN", 10), ("N", 11), ("ACGT", 12), ("RA", 13), ("NB", 14)])
 def test_random_against_oracle(eng, oracle, gen_pat, seed):
     """Larger general patterns (several tile waves, mixed radices) against the CPU oracle."""
     rng = np.random.default_rng(seed)
     _, nk, _ = oracle.plan_info(gen_pat)
     U = (1 + rng.negative_binomial(2, 2 / (2 + 800.0), size=nk)) * (rng.random(nk) < 0.9)
     M = rng.binomial(U, np.minimum(0.5, 0.02 * np.exp(rng.normal(0, 0.8, size=nk))))
+    U[0], M[0] = max(U[0], 50), max(M[0], 2)      # never an all-zero table (beta would be NaN)
     alpha, pen = 1.0, 4.0
     mu = M.sum() / (M.sum() + U.sum())
     beta = alpha * (1 - mu) / mu
@@ -165,6 +171,34 @@ def test_random_against_oracle(eng, oracle, gen_pat, seed):
     assert np.array_equal(_bits(best), _bits(ref["score"]))
     assert np.array_equal(split, ref["split"])
     assert np.array_equal(patnums, oracle.backtrack(gen_pat, ref["split"]))
+
+
+@pytest.mark.parametrize("gen_pat,seed", [("NNNNN", 21), ("RYNNANNKM", 22), ("VNNNH", 23), ("MMMMMMMMMM", 24),
+                                          ("RYNNNANRY", 25), ("BBDHVVB", 26), ("N", 27), ("ACGT", 28), ("NNNSNN", 29)])
+def test_random_cv_job_against_oracle(eng, oracle, gen_pat, seed):
+    """One held-out fold on larger / oddly shaped general patterns: train and held-out tables, both widths."""
+    rng = np.random.default_rng(seed)
+    _, nk, _ = oracle.plan_info(gen_pat)
+    U = (1 + rng.negative_binomial(2, 2 / (2 + 800.0), size=nk)) * (rng.random(nk) < 0.9)
+    M = rng.binomial(U, np.minimum(0.5, 0.02 * np.exp(rng.normal(0, 0.8, size=nk))))
+    if seed % 2:                      # provoke ties: few distinct values
+        U = rng.choice([0, 40, 80, 800], size=nk)
+        M = np.minimum(U, rng.choice([0, 1, 2, 4], size=nk))
+        M[0], U[0] = 3, 50
+    Mte, Ute = rng.binomial(M, 0.3), rng.binomial(U, 0.3)
+    alpha, pen = 1.0, 3.0
+    mu = (M.sum() - Mte.sum()) / ((M.sum() - Mte.sum()) + (U.sum() - Ute.sum()))
+    beta = alpha * (1 - mu) / mu
+    plan = eng.get_plan(gen_pat)
+    kM, kU = plan.upload_kmer_tables(M, U, name="r_tot")
+    tot = plan.expand(kM, kU, name="r_tot_e")
+    kMf, kUf = plan.upload_kmer_tables(Mte, Ute, name="r_fold")
+    fold = plan.expand(kMf, kUf, name="r_fold_e")
+    otr, ote = oracle.cv_job(gen_pat, M, U, Mte, Ute, alpha, beta, pen)
+    for mc in (int(M.sum() + U.sum()), 1 << 40):
+        train, test = plan.cv_job(tot[0], tot[1], fold[0], fold[1], mc, alpha, beta, pen, read_top=False)
+        assert np.array_equal(_bits(plan.gather(train)), _bits(otr))
+        assert np.array_equal(_bits(plan.gather(test)), _bits(ote))
 
 
 def test_7mer_test_data_final_dp(eng, oracle):

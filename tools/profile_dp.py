@@ -27,7 +27,7 @@ for rep in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     if kind == "single":
-        best, split = plan.dp_single(eM, eU, mc, 1.0, beta, 6.0)
+        best, kept = plan.dp_single(eM, eU, mc, 1.0, beta, 6.0)
     else:
         kMf, kUf = plan.upload_kmer_tables(pos // 5, neg // 5, name="pf")
         fM, fU = plan.expand(kMf, kUf, name="pfe")
