@@ -1,19 +1,29 @@
 // kp_kernels.cuh — sm_100a kernels of the pattern-partition DP.
 //
 // Work decomposition (geometry in kp_tables.h, rationale in DESIGN.md):
-//   * one WARP owns one tile at a time, one LANE owns one row of it, and the r0 (<= 15) sub-patterns of
-//     the register position of that row live in registers v[0..r0).  No block-wide barrier in steady state.
-//   * rows are visited in a precomputed schedule (rounds of <= 32 rows whose children are complete).
-//   * per row:  counts of the row's base k-mers (shared memory, int) -> subset sums in registers;
-//               running minimum over the HIGH-position splits, streamed from two child tiles each with
-//               coalesced 16-byte loads (HBM/L2);
-//               running minimum over the CROSS-row splits, from the tile's finished rows in shared memory;
-//               in-register splits of the register position interleaved with the float64 self-score
-//               (glibc-exact log) and the float64 compare / float32 store of the reference;
-//               one coalesced 16-byte store per group to the table, one 16-bit "kept whole" mask per row.
-//   * the single DP only keeps the minimum (fminf); which split won is recomputed by the backtrack
-//     from the stored scores (first split in scan order that reproduces the minimum).  The CV job needs
-//     the held-out loss of the winning split, so it tracks (value, scan rank) lexicographically.
+//
+//  K3  kp_score_kernel      float64 self-score of every pattern (glibc-exact log), embarrassingly
+//                           parallel, high occupancy.  A thread owns one row of one tile: counts of the row
+//                           from the tile's base k-mers (shared memory) by subset sums, then r0 scores.
+//                           It stores RN_f32(s) plus one "rounded up" bit per pattern; the reference's
+//                           float64 compare  s < (double)best  is exactly
+//                           sf < best || (sf == best && rounded_up)  with sf = RN_f32(s), and the value it
+//                           stores on a win is sf.  (CV: also the held-out loss of the unsplit pattern.)
+//
+//  K4  kp_dp_rows_kernel    the min-plus recurrence.  One WARP owns one tile at a time, one LANE owns one
+//                           row of it, the r0 (<= 15) sub-patterns of the register position live in
+//                           registers.  No block-wide barrier in steady state.  Rows are visited in a
+//                           precomputed schedule (rounds of <= 32 rows whose children are complete).
+//                           Per row: running minimum over the HIGH-position splits, streamed from two child
+//                           tiles each with coalesced 16-byte loads (software-pipelined two splits deep);
+//                           running minimum over the CROSS-row splits from the tile's finished rows in
+//                           shared memory; in-register splits of the register position interleaved with the
+//                           self-score compare; one coalesced 16-byte store per group, one 16-bit
+//                           "kept whole" mask per row.
+//                           The single DP only keeps the minimum (fminf); which split won is re-derived by
+//                           the backtrack from the stored scores (first split in scan order that reproduces
+//                           the minimum).  The CV job needs the held-out loss of the winning split, so it
+//                           tracks (value, scan rank) lexicographically.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -21,20 +31,9 @@
 #include "kp_math.cuh"
 #include "kp_tables.h"
 
-#define KP_MAX_WARPS 16
-
-struct KpDpParams {
-    const KpTables *tab;
-    const uint8_t *rowtab;
-    const uint32_t *tile_list;  // tiles of this wave, ascending
-    uint32_t ntiles_wave;
-    int leaf_wave;              // wave 0: rows of level 0 hold k-mers at the single-nucleotide digits
-    const long long *e0, *e1, *e2, *e3;  // single: M, U.  CV: Mtot, Utot, Mtest, Utest  [ntiles][tile_kmers]
-    double alpha, beta, penalty;
-    float *best;        // single: best loss;  CV: train loss
-    float *test;        // CV: held-out loss of the chosen partition
-    uint16_t *flags;    // single: per row, bit d set = pattern kept whole
-};
+#define KP_MAX_WARPS 14
+#define KP_SCORE_NT 256     // threads per CTA of the scoring kernel
+#define KP_SCORE_TPC 8      // tiles per chunk of the scoring kernel
 
 template <bool WIDE> struct KpCnt { typedef unsigned int type; };
 template <> struct KpCnt<true> { typedef unsigned long long type; };
@@ -73,31 +72,170 @@ __device__ __noinline__ void kp_leaf_cv_nl(unsigned long long Mtr, unsigned long
     *test = b;
 }
 
+// digit -> covered base digits of the register position (digit space), per radix
+__constant__ uint8_t kpc_bm1[4] = {1, 0, 0, 0};
+__constant__ uint8_t kpc_bm3[4] = {1, 2, 3, 0};
+__constant__ uint8_t kpc_bm7[8] = {1, 2, 4, 3, 5, 6, 7, 0};
+__constant__ uint8_t kpc_bm15[16] = {1, 2, 4, 8, 5, 10, 6, 9, 12, 3, 14, 13, 11, 7, 15, 0};
+
+template <int R0> __device__ __forceinline__ unsigned kp_bm(int d)
+{
+    return R0 == 15 ? kpc_bm15[d] : (R0 == 7 ? kpc_bm7[d] : (R0 == 3 ? kpc_bm3[d] : kpc_bm1[d]));
+}
+
 // ---------------------------------------------------------------------------------------------------
-// Per-row state and the in-register part of the recurrence.  Everything is indexed with compile-time
-// constants (macros below) so the arrays stay in registers.
+// K3: self-scores
 // ---------------------------------------------------------------------------------------------------
+struct KpScoreParams {
+    const KpTables *tab;
+    const uint8_t *rowtab;
+    const long long *e0, *e1, *e2, *e3;  // single: M, U.  CV: Mtot, Utot, Mtest, Utest  [ntiles][tile_kmers]
+    double alpha, beta, penalty;
+    float *self;        // RN_f32 of the self-score (train loss of the unsplit pattern)
+    float *tself;       // CV: held-out loss of the unsplit pattern
+    uint16_t *rup;      // per row: bit d set = RN_f32(s) > s
+};
+
 template <int R0, bool CV, bool WIDE>
-struct KpRow {
+__global__ void __launch_bounds__(KP_SCORE_NT) kp_score_kernel(const KpScoreParams p)
+{
     typedef typename KpCnt<WIDE>::type C;
-    static constexpr int NB = R0 == 15 ? 4 : (R0 == 7 ? 3 : (R0 == 3 ? 2 : 1));
-    static constexpr int NG = (R0 + 3) / 4;
-    float v[NG * 4];        // best (train) loss so far / final
-    float tv[CV ? NG * 4 : 1];   // CV: held-out loss of the current winner
-    int rk[CV ? NG * 4 : 1];     // CV: scan rank of the current winner (pos*8+j), 0x7fffffff = none yet
-    C m[NB], u[NB];         // counts of the row at the single-nucleotide digits of the register position
-    C mt[CV ? NB : 1], ut[CV ? NB : 1];
-    uint32_t flag;
+    constexpr int NB = R0 == 15 ? 4 : (R0 == 7 ? 3 : (R0 == 3 ? 2 : 1));
+    constexpr int NG = (R0 + 3) / 4;
+    constexpr int CW = CV ? 4 : 2;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const KpTables &tb = *p.tab;
+    const int nrows = tb.nrows, rp = tb.rp, nhigh = tb.nhigh;
+    const uint32_t tk = tb.tile_kmers, stride = tb.tile_stride, ntiles = tb.ntiles;
+    double2 *logtab = (double2 *)smem;
+    unsigned char *rt = smem + 2048;
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) logtab[i] = make_double2(kpc_logTab[2 * i], kpc_logTab[2 * i + 1]);
+    for (uint32_t i = threadIdx.x; i < tb.rt_bytes / 4; i += blockDim.x) ((uint32_t *)rt)[i] = ((const uint32_t *)p.rowtab)[i];
+    const uint8_t *row_level = rt + tb.rt_row_level;
+    const uint16_t *bs_off = (const uint16_t *)(rt + tb.rt_bs_off);
+    const uint16_t *bs = (const uint16_t *)(rt + tb.rt_bs);
+    C *bc = (C *)(rt + tb.rt_bytes);                                  // [TPC][tile_kmers][CW]
+    int *leaf_tile = (int *)((unsigned char *)bc + (size_t)KP_SCORE_TPC * tk * CW * sizeof(C));
+    const double alpha = p.alpha, beta = p.beta, penalty = p.penalty;
+
+    const uint32_t nchunks = (ntiles + KP_SCORE_TPC - 1) / KP_SCORE_TPC;
+    for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const uint32_t tile0 = chunk * KP_SCORE_TPC;
+        const uint32_t nt = min((uint32_t)KP_SCORE_TPC, ntiles - tile0);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nt * tk; i += blockDim.x) {
+            size_t g = (size_t)tile0 * tk + i;
+            if (!CV) {
+                bc[i * CW + 0] = (C)p.e0[g];
+                bc[i * CW + 1] = (C)p.e1[g];
+            } else {
+                long long mt = p.e2[g], ut = p.e3[g];
+                bc[i * CW + 0] = (C)(p.e0[g] - mt);  // train = total - held-out
+                bc[i * CW + 1] = (C)(p.e1[g] - ut);
+                bc[i * CW + 2] = (C)mt;
+                bc[i * CW + 3] = (C)ut;
+            }
+        }
+        if (threadIdx.x < nt) {  // a tile holds k-mers iff every high digit is a single nucleotide
+            uint32_t x = tile0 + threadIdx.x;
+            int leaf = 1;
+            for (int h = 0; h < nhigh; h++) {
+                int e = tb.highpos[h];
+                if (x % tb.radix[e] >= tb.nbase[e]) leaf = 0;
+                x /= tb.radix[e];
+            }
+            leaf_tile[threadIdx.x] = leaf;
+        }
+        __syncthreads();
+        for (uint32_t idx = threadIdx.x; idx < nt * (uint32_t)nrows; idx += blockDim.x) {
+            const uint32_t tl = idx / (uint32_t)nrows, srow = idx - tl * (uint32_t)nrows;
+            const uint32_t tile = tile0 + tl;
+            C m[NB], u[NB], mt[CV ? NB : 1], ut[CV ? NB : 1];
+#pragma unroll
+            for (int b = 0; b < NB; b++) { m[b] = 0; u[b] = 0; if (CV) { mt[b] = 0; ut[b] = 0; } }
+            const C *tbc = bc + (size_t)tl * tk * CW;
+            for (int i = bs_off[srow]; i < bs_off[srow + 1]; i++) {
+                const C *q = tbc + (size_t)bs[i] * NB * CW;
+#pragma unroll
+                for (int b = 0; b < NB; b++) {
+                    m[b] += q[b * CW + 0];
+                    u[b] += q[b * CW + 1];
+                    if (CV) { mt[b] += q[b * CW + 2]; ut[b] += q[b * CW + 3]; }
+                }
+            }
+            const bool leafrow = leaf_tile[tl] && row_level[srow] == 0;
+            float2 *os = (float2 *)(p.self + (size_t)tile * stride) + 2 * srow;
+            float2 *ot = CV ? (float2 *)(p.tself + (size_t)tile * stride) + 2 * srow : nullptr;
+            uint32_t rupm = 0;
+            // two patterns per iteration: enough ILP for the FP64 pipe, small enough for the instruction cache
+#pragma unroll 1
+            for (int h = 0; h < NG * 2; h++) {
+                float sf[2], tf[2];
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const int d = 2 * h + c;
+                    sf[c] = 0.f; tf[c] = 0.f;
+                    if (d < R0) {
+                        const unsigned bm = kp_bm<R0>(d);
+                        C M_ = 0, U_ = 0, Mt_ = 0, Ut_ = 0;
+#pragma unroll
+                        for (int b = 0; b < NB; b++)
+                            if ((bm >> b) & 1u) { M_ += m[b]; U_ += u[b]; if (CV) { Mt_ += mt[b]; Ut_ += ut[b]; } }
+                        double s_, t_ = 0.0, lp_, l1_;
+                        if (leafrow && d < NB) {
+                            if (!CV) s_ = kp_leaf_score_nl(M_, U_, alpha, beta, penalty, logtab);
+                            else kp_leaf_cv_nl(M_, U_, Mt_, Ut_, alpha, beta, penalty, logtab, &s_, &t_);
+                        } else {
+                            s_ = kp_self_score_t<C>(M_, U_, alpha, beta, penalty, logtab, lp_, l1_);
+                            if (CV) t_ = kp_test_ll((unsigned long long)Mt_, (unsigned long long)Ut_, lp_, l1_);
+                        }
+                        sf[c] = __double2float_rn(s_);
+                        if ((double)sf[c] > s_) rupm |= 1u << d;
+                        if (CV) tf[c] = __double2float_rn(t_);
+                    }
+                }
+                // element (d>>2, srow, d&3): float2 index ((h>>1)*rp + srow)*2 + (h&1)
+                os[(size_t)(h >> 1) * rp * 2 + (h & 1)] = make_float2(sf[0], sf[1]);
+                if (CV) ot[(size_t)(h >> 1) * rp * 2 + (h & 1)] = make_float2(tf[0], tf[1]);
+            }
+            p.rup[(size_t)tile * rp + srow] = (uint16_t)rupm;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4: min-plus recurrence
+// ---------------------------------------------------------------------------------------------------
+struct KpDpParams {
+    const KpTables *tab;
+    const uint8_t *rowtab;
+    const uint32_t *tile_list;  // tiles of this wave, ascending
+    uint32_t ntiles_wave;
+    const float *self;          // K3 outputs
+    const float *tself;
+    const uint16_t *rup;
+    float *best;        // single: best loss;  CV: train loss
+    float *test;        // CV: held-out loss of the chosen partition
+    uint16_t *flags;    // single: per row, bit d set = pattern kept whole
 };
 
 #define KP_NONE 0x7fffffff
 #define KP_FETCH 0x40000000  // CV: winner comes from a streamed or cross-row split; held-out value still to fetch
 
-template <int R0, bool CV, bool WIDE>
-struct KpRowOps {
-    typedef KpRow<R0, CV, WIDE> Row;
-    typedef typename Row::C C;
+template <int R0, bool CV>
+struct KpRow {
+    static constexpr int NG = (R0 + 3) / 4;
+    float v[NG * 4];             // best (train) loss so far / final
+    float sv[NG * 4];            // self-score (RN_f32)
+    float tv[CV ? NG * 4 : 1];   // CV: held-out loss of the current winner
+    float ts[CV ? NG * 4 : 1];   // CV: held-out loss of the unsplit pattern
+    int rk[CV ? NG * 4 : 1];     // CV: scan rank of the current winner (pos*8+j), KP_NONE = none yet
+    uint32_t rup, flag;
+};
 
+template <int R0, bool CV>
+struct KpRowOps {
+    typedef KpRow<R0, CV> Row;
     // one in-register split candidate of digit D with children A, B (J = split index in scan order)
     template <int D, int A, int B, int J>
     static __device__ __forceinline__ void split(Row &r, int rankbase)
@@ -111,63 +249,43 @@ struct KpRowOps {
             if (take) { r.v[D] = cand; r.rk[D] = rank; r.tv[D] = __fadd_rn(r.tv[A], r.tv[B]); }
         }
     }
-
-    // subset sum of the per-base counts for digit-space base mask BM
-    template <int BM>
-    static __device__ __forceinline__ C sum(const C *x)
-    {
-        C s = 0;
-#pragma unroll
-        for (int b = 0; b < Row::NB; b++)
-            if ((BM >> b) & 1) s += x[b];
-        return s;
-    }
 };
 
-template <int R0, bool CV, bool WIDE>
+template <int R0, bool CV>
 __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const KpDpParams p)
 {
-    typedef KpRow<R0, CV, WIDE> Row;
-    typedef KpRowOps<R0, CV, WIDE> Ops;
-    typedef typename Row::C C;
-    constexpr int NB = Row::NB, NG = Row::NG;
-    constexpr int CW = (CV ? 4 : 2);  // counters per base k-mer
+    typedef KpRow<R0, CV> Row;
+    typedef KpRowOps<R0, CV> Ops;
+    constexpr int NG = Row::NG;
 
     extern __shared__ __align__(16) unsigned char smem[];
     const KpTables &tb = *p.tab;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int rp = tb.rp, nrounds = tb.nrounds, nhigh = tb.nhigh;
-    const uint32_t tk = tb.tile_kmers, stride = tb.tile_stride;
+    const uint32_t stride = tb.tile_stride;
     const uint32_t rt_bytes = tb.rt_bytes;
 
-    double2 *logtab = (double2 *)smem;
-    unsigned char *rt = smem + 2048;
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) logtab[i] = make_double2(kpc_logTab[2 * i], kpc_logTab[2 * i + 1]);
+    unsigned char *rt = smem;
     for (uint32_t i = threadIdx.x; i < rt_bytes / 4; i += blockDim.x) ((uint32_t *)rt)[i] = ((const uint32_t *)p.rowtab)[i];
     __syncthreads();
     const uint16_t *round_start = (const uint16_t *)(rt + tb.rt_round_start);
-    const uint8_t *row_level = rt + tb.rt_row_level;
     const uint16_t *xs_off = (const uint16_t *)(rt + tb.rt_xs_off);
     const uint32_t *xs = (const uint32_t *)(rt + tb.rt_xs);
     const uint8_t *xsr = rt + tb.rt_xs_rank;
-    const uint16_t *bs_off = (const uint16_t *)(rt + tb.rt_bs_off);
-    const uint16_t *bs = (const uint16_t *)(rt + tb.rt_bs);
 
-    unsigned char *wm = smem + 2048 + rt_bytes + (size_t)warp * tb.warp_smem_bytes[CV][WIDE];
+    unsigned char *wm = smem + rt_bytes + (size_t)warp * tb.warp_smem_bytes;
     float4 *S = (float4 *)wm;                                  // [NG][rp]
-    C *bc = (C *)(wm + (size_t)NG * rp * 16);                  // [tile_kmers][CW]
-    uint32_t *hs1 = (uint32_t *)((unsigned char *)bc + (size_t)tk * CW * sizeof(C));
+    uint32_t *hs1 = (uint32_t *)(wm + (size_t)NG * rp * 16);
     uint32_t *hs2 = hs1 + KP_MAXHS;
     uint8_t *hsr = (uint8_t *)(hs2 + KP_MAXHS);
     int *s_nhs = (int *)(hsr + KP_MAXHS);
 
-    const double alpha = p.alpha, beta = p.beta, penalty = p.penalty;
     const float INF = __int_as_float(0x7f800000);
     const int rankbase = tb.estar >= 0 ? tb.pos_id[tb.estar] * 8 : 0;
 
     for (uint32_t it = blockIdx.x * nwarps + warp; it < p.ntiles_wave; it += gridDim.x * nwarps) {
         const uint32_t tile = p.tile_list[it];
-        __syncwarp();  // previous tile's readers of S / bc / hs are done
+        __syncwarp();  // previous tile's readers of S / hs are done
         // ---- the tile's high-position splits, in scan order ----
         {
             int ns = 0, d = 0, e = 0;
@@ -195,71 +313,71 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
             }
             if (lane == 0) *s_nhs = total;
         }
-        // ---- base counts of the tile ----
-        for (uint32_t kl = lane; kl < tk; kl += 32) {
-            size_t g = (size_t)tile * tk + kl;
-            if (!CV) {
-                bc[kl * CW + 0] = (C)p.e0[g];
-                bc[kl * CW + 1] = (C)p.e1[g];
-            } else {
-                long long mt = p.e2[g], ut = p.e3[g];
-                bc[kl * CW + 0] = (C)(p.e0[g] - mt);  // train = total - held-out
-                bc[kl * CW + 1] = (C)(p.e1[g] - ut);
-                bc[kl * CW + 2] = (C)mt;
-                bc[kl * CW + 3] = (C)ut;
-            }
-        }
         __syncwarp();
         const int nhs = *s_nhs;
         const float *tbase = p.best;
         float4 *otile = (float4 *)(p.best + (size_t)tile * stride);
+        const float4 *stile = (const float4 *)(p.self + (size_t)tile * stride);
 
         for (int rnd = 0; rnd < nrounds; rnd++) {
             const int srow = round_start[rnd] + lane;
             if (srow < round_start[rnd + 1]) {
                 Row r;
                 r.flag = 0;
-                // ---- counts of this row at the single-nucleotide digits ----
+                // self-scores of the row: issued first, consumed last
 #pragma unroll
-                for (int b = 0; b < NB; b++) { r.m[b] = 0; r.u[b] = 0; if (CV) { r.mt[b] = 0; r.ut[b] = 0; } }
-                for (int i = bs_off[srow]; i < bs_off[srow + 1]; i++) {
-                    const C *q = bc + (size_t)bs[i] * NB * CW;
-#pragma unroll
-                    for (int b = 0; b < NB; b++) {
-                        r.m[b] += q[b * CW + 0];
-                        r.u[b] += q[b * CW + 1];
-                        if (CV) { r.mt[b] += q[b * CW + 2]; r.ut[b] += q[b * CW + 3]; }
+                for (int g = 0; g < NG; g++) {
+                    float4 x = __ldg(stile + g * rp + srow);
+                    r.sv[4 * g] = x.x; r.sv[4 * g + 1] = x.y; r.sv[4 * g + 2] = x.z; r.sv[4 * g + 3] = x.w;
+                    if (CV) {
+                        float4 y = __ldg((const float4 *)(p.tself + (size_t)tile * stride) + g * rp + srow);
+                        r.ts[4 * g] = y.x; r.ts[4 * g + 1] = y.y; r.ts[4 * g + 2] = y.z; r.ts[4 * g + 3] = y.w;
                     }
                 }
+                r.rup = p.rup[(size_t)tile * rp + srow];
 #pragma unroll
                 for (int c = 0; c < NG * 4; c++) { r.v[c] = INF; if (CV) { r.tv[c] = 0.f; r.rk[c] = KP_NONE; } }
 
-                // ---- high-position splits: stream two child tiles per split ----
-                for (int s = 0; s < nhs; s++) {
-                    const float4 *a = (const float4 *)(tbase + (size_t)hs1[s] * stride) + srow;
-                    const float4 *b = (const float4 *)(tbase + (size_t)hs2[s] * stride) + srow;
-                    float4 xa[NG], xb[NG];
-#pragma unroll
-                    for (int g = 0; g < NG; g++) { xa[g] = __ldg(a + g * rp); xb[g] = __ldg(b + g * rp); }
-                    const int rank = CV ? (int)hsr[s] : 0;
-#pragma unroll
-                    for (int g = 0; g < NG; g++) {
-                        float c0 = __fadd_rn(xa[g].x, xb[g].x), c1 = __fadd_rn(xa[g].y, xb[g].y);
-                        float c2 = __fadd_rn(xa[g].z, xb[g].z), c3 = __fadd_rn(xa[g].w, xb[g].w);
-                        if (!CV) {
-                            r.v[4 * g + 0] = fminf(r.v[4 * g + 0], c0);
-                            r.v[4 * g + 1] = fminf(r.v[4 * g + 1], c1);
-                            r.v[4 * g + 2] = fminf(r.v[4 * g + 2], c2);
-                            r.v[4 * g + 3] = fminf(r.v[4 * g + 3], c3);
-                        } else {
-                            // hs is in scan order: a strict '<' keeps the earliest split among equals
-                            if (c0 < r.v[4 * g + 0]) { r.v[4 * g + 0] = c0; r.rk[4 * g + 0] = rank | KP_FETCH; }
-                            if (c1 < r.v[4 * g + 1]) { r.v[4 * g + 1] = c1; r.rk[4 * g + 1] = rank | KP_FETCH; }
-                            if (c2 < r.v[4 * g + 2]) { r.v[4 * g + 2] = c2; r.rk[4 * g + 2] = rank | KP_FETCH; }
-                            if (c3 < r.v[4 * g + 3]) { r.v[4 * g + 3] = c3; r.rk[4 * g + 3] = rank | KP_FETCH; }
-                        }
+                // ---- high-position splits: stream two child tiles per split, two splits in flight ----
+#define KP_HS_LOAD(s, xa, xb)                                                                        \
+    {                                                                                                \
+        const float4 *a_ = (const float4 *)(tbase + (size_t)hs1[s] * stride) + srow;                 \
+        const float4 *b_ = (const float4 *)(tbase + (size_t)hs2[s] * stride) + srow;                 \
+        _Pragma("unroll") for (int g = 0; g < NG; g++) { xa[g] = __ldg(a_ + g * rp); xb[g] = __ldg(b_ + g * rp); } \
+    }
+#define KP_HS_USE(s, xa, xb)                                                                         \
+    {                                                                                                \
+        const int rank = CV ? (int)hsr[s] : 0;                                                       \
+        _Pragma("unroll") for (int g = 0; g < NG; g++) {                                             \
+            float c0 = __fadd_rn(xa[g].x, xb[g].x), c1 = __fadd_rn(xa[g].y, xb[g].y);                \
+            float c2 = __fadd_rn(xa[g].z, xb[g].z), c3 = __fadd_rn(xa[g].w, xb[g].w);                \
+            if (!CV) {                                                                               \
+                r.v[4 * g + 0] = fminf(r.v[4 * g + 0], c0);                                          \
+                r.v[4 * g + 1] = fminf(r.v[4 * g + 1], c1);                                          \
+                r.v[4 * g + 2] = fminf(r.v[4 * g + 2], c2);                                          \
+                r.v[4 * g + 3] = fminf(r.v[4 * g + 3], c3);                                          \
+            } else { /* hs is in scan order: a strict '<' keeps the earliest split among equals */   \
+                if (c0 < r.v[4 * g + 0]) { r.v[4 * g + 0] = c0; r.rk[4 * g + 0] = rank | KP_FETCH; } \
+                if (c1 < r.v[4 * g + 1]) { r.v[4 * g + 1] = c1; r.rk[4 * g + 1] = rank | KP_FETCH; } \
+                if (c2 < r.v[4 * g + 2]) { r.v[4 * g + 2] = c2; r.rk[4 * g + 2] = rank | KP_FETCH; } \
+                if (c3 < r.v[4 * g + 3]) { r.v[4 * g + 3] = c3; r.rk[4 * g + 3] = rank | KP_FETCH; } \
+            }                                                                                        \
+        }                                                                                            \
+    }
+                {
+                    float4 xa0[NG], xb0[NG], xa1[NG], xb1[NG];
+                    int s = 0;
+                    if (nhs > 0) KP_HS_LOAD(0, xa0, xb0)
+                    for (; s + 2 <= nhs; s += 2) {
+                        KP_HS_LOAD(s + 1, xa1, xb1)
+                        KP_HS_USE(s, xa0, xb0)
+                        if (s + 2 < nhs) KP_HS_LOAD(s + 2, xa0, xb0)
+                        KP_HS_USE(s + 1, xa1, xb1)
                     }
+                    if (s < nhs) KP_HS_USE(s, xa0, xb0)
                 }
+#undef KP_HS_LOAD
+#undef KP_HS_USE
                 // ---- cross-row splits: finished rows of this tile, shared memory ----
                 for (int i = xs_off[srow]; i < xs_off[srow + 1]; i++) {
                     const uint32_t pr = xs[i];
@@ -285,8 +403,7 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
                     }
                 }
 
-                // ---- register position: in-register splits + self-score, digit by digit ----
-                const bool leafrow = p.leaf_wave && row_level[srow] == 0;
+                // ---- register position: in-register splits + self-score compare, digit by digit ----
                 // CV: fetch the held-out loss of a winner that came from memory (streamed or cross-row split)
                 auto fetch_test = [&](int d, int rank) -> float {
                     const int inrow = ((d >> 2) * rp) * 4 + (d & 3);
@@ -301,54 +418,43 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
                                              __ldg(p.test + (size_t)hs2[s] * stride + inrow + srow * 4));
                     return 0.f;
                 };
-#define KP_FIN(D, BM)                                                                                            \
+                // reference: if s < (double)best: best = f32(s)   <=>   sf < best || (sf == best && sf > s)
+#define KP_FIN(D)                                                                                                \
     {                                                                                                            \
-        C M_ = Ops::template sum<BM>(r.m), U_ = Ops::template sum<BM>(r.u);                                      \
-        double s_, lp_ = 0.0, l1_ = 0.0, t_ = 0.0;                                                               \
-        const bool leaf_ = leafrow && (D) < NB;                                                                  \
+        const bool self_ = r.sv[D] < r.v[D] || (r.sv[D] == r.v[D] && ((r.rup >> (D)) & 1u));                     \
         if (!CV) {                                                                                               \
-            if (leaf_) s_ = (double)__double2float_rn(kp_leaf_score_nl(M_, U_, alpha, beta, penalty, logtab));   \
-            else s_ = kp_self_score_t<C>(M_, U_, alpha, beta, penalty, logtab, lp_, l1_);                        \
-            if (s_ < (double)r.v[D]) { r.v[D] = __double2float_rn(s_); r.flag |= 1u << (D); }                    \
+            if (self_) { r.v[D] = r.sv[D]; r.flag |= 1u << (D); }                                                \
         } else {                                                                                                 \
-            C Mt_ = Ops::template sum<BM>(r.mt), Ut_ = Ops::template sum<BM>(r.ut);                              \
-            if (leaf_) {                                                                                         \
-                kp_leaf_cv_nl(M_, U_, Mt_, Ut_, alpha, beta, penalty, logtab, &s_, &t_);                         \
-                s_ = (double)__double2float_rn(s_);                                                              \
-            } else {                                                                                             \
-                s_ = kp_self_score_t<C>(M_, U_, alpha, beta, penalty, logtab, lp_, l1_);                         \
-                t_ = kp_test_ll((unsigned long long)Mt_, (unsigned long long)Ut_, lp_, l1_);                     \
-            }                                                                                                    \
-            if (s_ < (double)r.v[D]) { r.v[D] = __double2float_rn(s_); r.tv[D] = __double2float_rn(t_); }        \
+            if (self_) { r.v[D] = r.sv[D]; r.tv[D] = r.ts[D]; }                                                  \
             else if (r.rk[D] & KP_FETCH) r.tv[D] = fetch_test(D, r.rk[D] & ~KP_FETCH);                           \
         }                                                                                                        \
     }
 #define KP_SP(D, A, B, J) Ops::template split<D, A, B, J>(r, rankbase);
                 if (R0 == 1) {
-                    KP_FIN(0, 1)
+                    KP_FIN(0)
                 } else if (R0 == 3) {
-                    KP_FIN(0, 1) KP_FIN(1, 2)
-                    KP_SP(2, 0, 1, 0) KP_FIN(2, 3)
+                    KP_FIN(0) KP_FIN(1)
+                    KP_SP(2, 0, 1, 0) KP_FIN(2)
                 } else if (R0 == 7) {
-                    KP_FIN(0, 1) KP_FIN(1, 2) KP_FIN(2, 4)
-                    KP_SP(3, 0, 1, 0) KP_FIN(3, 3)
-                    KP_SP(4, 0, 2, 0) KP_FIN(4, 5)
-                    KP_SP(5, 1, 2, 0) KP_FIN(5, 6)
-                    KP_SP(6, 0, 5, 0) KP_SP(6, 1, 4, 1) KP_SP(6, 2, 3, 2) KP_FIN(6, 7)
+                    KP_FIN(0) KP_FIN(1) KP_FIN(2)
+                    KP_SP(3, 0, 1, 0) KP_FIN(3)
+                    KP_SP(4, 0, 2, 0) KP_FIN(4)
+                    KP_SP(5, 1, 2, 0) KP_FIN(5)
+                    KP_SP(6, 0, 5, 0) KP_SP(6, 1, 4, 1) KP_SP(6, 2, 3, 2) KP_FIN(6)
                 } else {
-                    KP_FIN(0, 1) KP_FIN(1, 2) KP_FIN(2, 4) KP_FIN(3, 8)
-                    KP_SP(4, 0, 2, 0) KP_FIN(4, 5)     // R = A|G
-                    KP_SP(5, 1, 3, 0) KP_FIN(5, 10)    // Y = C|T
-                    KP_SP(6, 2, 1, 0) KP_FIN(6, 6)     // S = G|C
-                    KP_SP(7, 0, 3, 0) KP_FIN(7, 9)     // W = A|T
-                    KP_SP(8, 2, 3, 0) KP_FIN(8, 12)    // K = G|T
-                    KP_SP(9, 0, 1, 0) KP_FIN(9, 3)     // M = A|C
-                    KP_SP(10, 1, 8, 0) KP_SP(10, 2, 5, 1) KP_SP(10, 3, 6, 2) KP_FIN(10, 14)   // B
-                    KP_SP(11, 0, 8, 0) KP_SP(11, 2, 7, 1) KP_SP(11, 3, 4, 2) KP_FIN(11, 13)   // D
-                    KP_SP(12, 0, 5, 0) KP_SP(12, 1, 7, 1) KP_SP(12, 3, 9, 2) KP_FIN(12, 11)   // H
-                    KP_SP(13, 0, 6, 0) KP_SP(13, 1, 4, 1) KP_SP(13, 2, 9, 2) KP_FIN(13, 7)    // V
+                    KP_FIN(0) KP_FIN(1) KP_FIN(2) KP_FIN(3)
+                    KP_SP(4, 0, 2, 0) KP_FIN(4)     // R = A|G
+                    KP_SP(5, 1, 3, 0) KP_FIN(5)     // Y = C|T
+                    KP_SP(6, 2, 1, 0) KP_FIN(6)     // S = G|C
+                    KP_SP(7, 0, 3, 0) KP_FIN(7)     // W = A|T
+                    KP_SP(8, 2, 3, 0) KP_FIN(8)     // K = G|T
+                    KP_SP(9, 0, 1, 0) KP_FIN(9)     // M = A|C
+                    KP_SP(10, 1, 8, 0) KP_SP(10, 2, 5, 1) KP_SP(10, 3, 6, 2) KP_FIN(10)   // B
+                    KP_SP(11, 0, 8, 0) KP_SP(11, 2, 7, 1) KP_SP(11, 3, 4, 2) KP_FIN(11)   // D
+                    KP_SP(12, 0, 5, 0) KP_SP(12, 1, 7, 1) KP_SP(12, 3, 9, 2) KP_FIN(12)   // H
+                    KP_SP(13, 0, 6, 0) KP_SP(13, 1, 4, 1) KP_SP(13, 2, 9, 2) KP_FIN(13)   // V
                     KP_SP(14, 6, 7, 0) KP_SP(14, 8, 9, 1) KP_SP(14, 4, 5, 2) KP_SP(14, 0, 10, 3)
-                    KP_SP(14, 1, 11, 4) KP_SP(14, 2, 12, 5) KP_SP(14, 3, 13, 6) KP_FIN(14, 15)  // N
+                    KP_SP(14, 1, 11, 4) KP_SP(14, 2, 12, 5) KP_SP(14, 3, 13, 6) KP_FIN(14)  // N
                 }
 #undef KP_FIN
 #undef KP_SP
