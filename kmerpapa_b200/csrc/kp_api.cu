@@ -39,6 +39,7 @@ struct kp_plan {
     uint32_t *d_tiles = nullptr;
     uint8_t *d_genmask = nullptr;
     int *d_err = nullptr;
+    uint32_t *d_counters = nullptr;  // one tile counter per wave
     uint64_t launches = 0;
     int nwarps = 0;          // warps (= tiles in flight) per CTA of the DP kernel
     size_t smem_optin = 0;
@@ -118,6 +119,7 @@ int kp_plan_create(const char *gen_pat, int device, kp_plan **out)
     KP_CUDA(cudaMemcpy(p->d_genmask, p->host.gen_mask, KP_MAXK, cudaMemcpyHostToDevice));
     KP_CUDA(cudaMalloc(&p->d_err, sizeof(int)));
     KP_CUDA(cudaMemset(p->d_err, 0, sizeof(int)));
+    KP_CUDA(cudaMalloc(&p->d_counters, sizeof(uint32_t) * 64));
     p->smem_optin = prop.sharedMemPerBlockOptin;
     {
         size_t fixed = t.rt_bytes, per_warp = t.warp_smem_bytes;
@@ -150,6 +152,7 @@ int kp_plan_destroy(kp_plan *p)
     cudaFree(p->d_tiles);
     cudaFree(p->d_genmask);
     cudaFree(p->d_err);
+    cudaFree(p->d_counters);
     delete p;
     return 0;
 }
@@ -272,11 +275,14 @@ static int launch_dp(kp_plan *p, bool cv, KpDpParams prm, cudaStream_t st)
     if (nw < 1) return fail("DP kernel does not fit in shared memory for this tile shape");
     size_t nhl = p->host.hl_off.size() - 1;
     const KpTables &t = p->host.t;
+    if (nhl > 64) return fail("too many tile waves");
+    KP_CUDA(cudaMemsetAsync(p->d_counters, 0, sizeof(uint32_t) * 64, st));
     for (size_t l = 0; l < nhl; l++) {
         uint64_t lo = p->host.hl_off[l], hi = p->host.hl_off[l + 1];
         if (hi == lo) continue;
         prm.tile_list = p->d_tiles + lo;
         prm.ntiles_wave = (uint32_t)(hi - lo);
+        prm.counter = p->d_counters + l;
         uint64_t ntile = hi - lo;
         int warps = nw;
         if (ntile < (uint64_t)p->sm_count * nw) {  // small wave: spread the tiles over all SMs

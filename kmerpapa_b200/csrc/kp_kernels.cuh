@@ -211,6 +211,7 @@ struct KpDpParams {
     const uint8_t *rowtab;
     const uint32_t *tile_list;  // tiles of this wave, ascending
     uint32_t ntiles_wave;
+    uint32_t *counter;          // next unclaimed entry of tile_list (zeroed before the launch)
     const float *self;          // K3 outputs
     const float *tself;
     const uint16_t *rup;
@@ -283,7 +284,14 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
     const float INF = __int_as_float(0x7f800000);
     const int rankbase = tb.estar >= 0 ? tb.pos_id[tb.estar] * 8 : 0;
 
-    for (uint32_t it = blockIdx.x * nwarps + warp; it < p.ntiles_wave; it += gridDim.x * nwarps) {
+    // Tiles are claimed in list order (ascending tile number): the tiles in flight on the whole GPU are then
+    // always neighbours in the pattern lattice, which share child tiles, so those re-reads hit in L2.
+    (void)nwarps;
+    for (;;) {
+        uint32_t it = 0;
+        if (lane == 0) it = atomicAdd(p.counter, 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= p.ntiles_wave) break;
         const uint32_t tile = p.tile_list[it];
         __syncwarp();  // previous tile's readers of S / hs are done
         // ---- the tile's high-position splits, in scan order ----
@@ -319,26 +327,9 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
         float4 *otile = (float4 *)(p.best + (size_t)tile * stride);
         const float4 *stile = (const float4 *)(p.self + (size_t)tile * stride);
 
-        for (int rnd = 0; rnd < nrounds; rnd++) {
-            const int srow = round_start[rnd] + lane;
-            if (srow < round_start[rnd + 1]) {
-                Row r;
-                r.flag = 0;
-                // self-scores of the row: issued first, consumed last
-#pragma unroll
-                for (int g = 0; g < NG; g++) {
-                    float4 x = __ldg(stile + g * rp + srow);
-                    r.sv[4 * g] = x.x; r.sv[4 * g + 1] = x.y; r.sv[4 * g + 2] = x.z; r.sv[4 * g + 3] = x.w;
-                    if (CV) {
-                        float4 y = __ldg((const float4 *)(p.tself + (size_t)tile * stride) + g * rp + srow);
-                        r.ts[4 * g] = y.x; r.ts[4 * g + 1] = y.y; r.ts[4 * g + 2] = y.z; r.ts[4 * g + 3] = y.w;
-                    }
-                }
-                r.rup = p.rup[(size_t)tile * rp + srow];
-#pragma unroll
-                for (int c = 0; c < NG * 4; c++) { r.v[c] = INF; if (CV) { r.tv[c] = 0.f; r.rk[c] = KP_NONE; } }
-
-                // ---- high-position splits: stream two child tiles per split, two splits in flight ----
+        // ---- phase D (single DP): stream the child tiles of the high-position splits for ALL rows of the tile,
+        //      32 consecutive rows at a time, two splits in flight; the running minimum of row r is parked
+        //      in S[r] until the row's turn in the schedule ----
 #define KP_HS_LOAD(s, xa, xb)                                                                        \
     {                                                                                                \
         const float4 *a_ = (const float4 *)(tbase + (size_t)hs1[s] * stride) + srow;                 \
@@ -364,20 +355,61 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
             }                                                                                        \
         }                                                                                            \
     }
-                {
-                    float4 xa0[NG], xb0[NG], xa1[NG], xb1[NG];
-                    int s = 0;
-                    if (nhs > 0) KP_HS_LOAD(0, xa0, xb0)
-                    for (; s + 2 <= nhs; s += 2) {
-                        KP_HS_LOAD(s + 1, xa1, xb1)
-                        KP_HS_USE(s, xa0, xb0)
-                        if (s + 2 < nhs) KP_HS_LOAD(s + 2, xa0, xb0)
-                        KP_HS_USE(s + 1, xa1, xb1)
+#define KP_HS_STREAM()                                                                               \
+    {                                                                                                \
+        float4 xa0[NG], xb0[NG], xa1[NG], xb1[NG];                                                   \
+        int s = 0;                                                                                   \
+        if (nhs > 0) KP_HS_LOAD(0, xa0, xb0)                                                         \
+        for (; s + 2 <= nhs; s += 2) {                                                               \
+            KP_HS_LOAD(s + 1, xa1, xb1)                                                              \
+            KP_HS_USE(s, xa0, xb0)                                                                   \
+            if (s + 2 < nhs) KP_HS_LOAD(s + 2, xa0, xb0)                                             \
+            KP_HS_USE(s + 1, xa1, xb1)                                                               \
+        }                                                                                            \
+        if (s < nhs) KP_HS_USE(s, xa0, xb0)                                                          \
+    }
+        if (!CV) {
+            for (int srow = lane; srow < tb.nrows; srow += 32) {
+                Row r;
+#pragma unroll
+                for (int c = 0; c < NG * 4; c++) r.v[c] = INF;
+                KP_HS_STREAM()
+#pragma unroll
+                for (int g = 0; g < NG; g++)
+                    S[g * rp + srow] = make_float4(r.v[4 * g], r.v[4 * g + 1], r.v[4 * g + 2], r.v[4 * g + 3]);
+            }
+            __syncwarp();
+        }
+
+        for (int rnd = 0; rnd < nrounds; rnd++) {
+            const int srow = round_start[rnd] + lane;
+            if (srow < round_start[rnd + 1]) {
+                Row r;
+                r.flag = 0;
+                // self-scores of the row: issued first, consumed last
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+                    float4 x = __ldcs(stile + g * rp + srow);  // read once: evict first
+                    r.sv[4 * g] = x.x; r.sv[4 * g + 1] = x.y; r.sv[4 * g + 2] = x.z; r.sv[4 * g + 3] = x.w;
+                    if (CV) {
+                        float4 y = __ldcs((const float4 *)(p.tself + (size_t)tile * stride) + g * rp + srow);
+                        r.ts[4 * g] = y.x; r.ts[4 * g + 1] = y.y; r.ts[4 * g + 2] = y.z; r.ts[4 * g + 3] = y.w;
                     }
-                    if (s < nhs) KP_HS_USE(s, xa0, xb0)
                 }
-#undef KP_HS_LOAD
-#undef KP_HS_USE
+                r.rup = p.rup[(size_t)tile * rp + srow];
+#pragma unroll
+                for (int c = 0; c < NG * 4; c++) { r.v[c] = INF; if (CV) { r.tv[c] = 0.f; r.rk[c] = KP_NONE; } }
+
+                if (CV) {
+                    // ---- high-position splits: stream two child tiles per split, two splits in flight ----
+                    KP_HS_STREAM()
+                } else {
+#pragma unroll
+                    for (int g = 0; g < NG; g++) {  // minimum over the high-position splits, parked by phase D
+                        float4 x = S[g * rp + srow];
+                        r.v[4 * g] = x.x; r.v[4 * g + 1] = x.y; r.v[4 * g + 2] = x.z; r.v[4 * g + 3] = x.w;
+                    }
+                }
                 // ---- cross-row splits: finished rows of this tile, shared memory ----
                 for (int i = xs_off[srow]; i < xs_off[srow + 1]; i++) {
                     const uint32_t pr = xs[i];
@@ -465,7 +497,7 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
                 for (int g = 0; g < NG; g++) {
                     float4 o = make_float4(r.v[4 * g], r.v[4 * g + 1], r.v[4 * g + 2], r.v[4 * g + 3]);
                     S[g * rp + srow] = o;
-                    otile[g * rp + srow] = o;
+                    __stcs(otile + g * rp + srow, o);  // next read is a whole wave away: do not keep it in L2
                     if (CV) {
                         float4 ot = make_float4(r.tv[4 * g], r.tv[4 * g + 1], r.tv[4 * g + 2], r.tv[4 * g + 3]);
                         ((float4 *)(p.test + (size_t)tile * stride))[g * rp + srow] = ot;
@@ -476,6 +508,9 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
             __syncwarp();  // rows of this round (shared S, and for CV the global test rows) visible to the warp
         }
     }
+#undef KP_HS_LOAD
+#undef KP_HS_USE
+#undef KP_HS_STREAM
 }
 
 // ---------------------------------------------------------------------------------------------------
