@@ -41,19 +41,57 @@ template <> struct KpCnt<true> { typedef unsigned long long type; };
 __device__ __forceinline__ double kp_cnt2d(unsigned int x) { return __uint2double_rn(x); }
 __device__ __forceinline__ double kp_cnt2d(unsigned long long x) { return __ull2double_rn(x); }
 
-// level >= 1 self-score (w_numba.py:56-61 / _CV.py:60-70), templated on the on-chip count width
+// level >= 1 self-score (w_numba.py:56-61 / _CV.py:60-70), templated on the on-chip count width.
+// log p takes the table path and log(1-p) the near-1 polynomial for every realistic rate; anything else
+// (p >= 0.9375, p == 0, 1-p == 1, ...) goes through the out-of-line generic log.  No branches on M, U:
+// the unselected products may be NaN/inf and are discarded by the selects.
 template <typename C>
 __device__ __forceinline__ double kp_self_score_t(C M, C U, double alpha, double beta, double penalty,
-                                                  const double2 *tab, double &logp, double &log1mp)
+                                                  const double2 *tab, const KpLogK &K, double &logp, double &log1mp)
 {
     double Md = kp_cnt2d(M), Ud = kp_cnt2d(U);
     double p = __ddiv_rn(KP_ADD(Md, alpha), KP_ADD(KP_ADD(kp_cnt2d((C)(M + U)), alpha), beta));
-    logp = kp_log(p, tab);
-    log1mp = kp_log(KP_SUB(1.0, p), tab);
-    double s = penalty;
-    if (M > 0) s = KP_ADD(s, KP_MUL(KP_MUL(-2.0, Md), logp));
-    if (U > 0) s = KP_ADD(s, KP_MUL(KP_MUL(-2.0, Ud), log1mp));
+    double q = KP_SUB(1.0, p);
+    int phi = __double2hiint(p), qhi = __double2hiint(q), qlo = __double2loint(q);
+    if (kp_log_is_plain(phi) && !kp_log_is_near1(phi)) logp = kp_log_main(phi, __double2loint(p), tab, K);
+    else logp = kp_log_slow(p, tab);
+    if (kp_log_is_near1(qhi) && !(qhi == 0x3ff00000 && qlo == 0)) log1mp = kp_log_near1(q, K);
+    else log1mp = kp_log_slow(q, tab);
+    double s1 = KP_ADD(penalty, KP_MUL(KP_MUL(-2.0, Md), logp));
+    double s = M > 0 ? s1 : penalty;
+    double s2 = KP_ADD(s, KP_MUL(KP_MUL(-2.0, Ud), log1mp));
+    return U > 0 ? s2 : s;
+}
+
+// held-out -2 log-lik of a pattern kept whole (_CV.py:73-78), branch-free
+template <typename C>
+__device__ __forceinline__ double kp_test_ll_t(C Mt, C Ut, double logp, double log1mp)
+{
+    double t1 = KP_ADD(0.0, KP_MUL(KP_MUL(-2.0, kp_cnt2d(Mt)), logp));
+    double t = Mt > 0 ? t1 : 0.0;
+    double t2 = KP_ADD(t, KP_MUL(KP_MUL(-2.0, kp_cnt2d(Ut)), log1mp));
+    return Ut > 0 ? t2 : t;
+}
+
+// subset sum of per-base counts for a compile-time base mask
+template <int BM, int NB, typename C>
+__device__ __forceinline__ C kp_sum_bases(const C *x)
+{
+    C s = 0;
+#pragma unroll
+    for (int b = 0; b < NB; b++)
+        if ((BM >> b) & 1) s += x[b];
     return s;
+}
+
+// digit -> covered base digits of the register position (digit space), per radix
+template <int R0> __host__ __device__ constexpr int kp_bm_c(int d)
+{
+    return R0 == 15 ? (d == 0 ? 1 : d == 1 ? 2 : d == 2 ? 4 : d == 3 ? 8 : d == 4 ? 5 : d == 5 ? 10 : d == 6 ? 6 : d == 7 ? 9 :
+                       d == 8 ? 12 : d == 9 ? 3 : d == 10 ? 14 : d == 11 ? 13 : d == 12 ? 11 : d == 13 ? 7 : d == 14 ? 15 : 0)
+         : R0 == 7 ? (d == 0 ? 1 : d == 1 ? 2 : d == 2 ? 4 : d == 3 ? 3 : d == 4 ? 5 : d == 5 ? 6 : d == 6 ? 7 : 0)
+         : R0 == 3 ? (d == 0 ? 1 : d == 1 ? 2 : d == 2 ? 3 : 0)
+         : (d == 0 ? 1 : 0);
 }
 
 // level-0 scores are rare (k-mers only): keep them out of line
@@ -70,17 +108,6 @@ __device__ __noinline__ void kp_leaf_cv_nl(unsigned long long Mtr, unsigned long
     kp_leaf_cv(Mtr, Utr, Mte, Ute, alpha, beta, penalty, tab, a, b);
     *train = a;
     *test = b;
-}
-
-// digit -> covered base digits of the register position (digit space), per radix
-__constant__ uint8_t kpc_bm1[4] = {1, 0, 0, 0};
-__constant__ uint8_t kpc_bm3[4] = {1, 2, 3, 0};
-__constant__ uint8_t kpc_bm7[8] = {1, 2, 4, 3, 5, 6, 7, 0};
-__constant__ uint8_t kpc_bm15[16] = {1, 2, 4, 8, 5, 10, 6, 9, 12, 3, 14, 13, 11, 7, 15, 0};
-
-template <int R0> __device__ __forceinline__ unsigned kp_bm(int d)
-{
-    return R0 == 15 ? kpc_bm15[d] : (R0 == 7 ? kpc_bm7[d] : (R0 == 3 ? kpc_bm3[d] : kpc_bm1[d]));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -117,6 +144,7 @@ __global__ void __launch_bounds__(KP_SCORE_NT) kp_score_kernel(const KpScorePara
     C *bc = (C *)(rt + tb.rt_bytes);                                  // [TPC][tile_kmers][CW]
     int *leaf_tile = (int *)((unsigned char *)bc + (size_t)KP_SCORE_TPC * tk * CW * sizeof(C));
     const double alpha = p.alpha, beta = p.beta, penalty = p.penalty;
+    const KpLogK K = kp_logk_load();
 
     const uint32_t nchunks = (ntiles + KP_SCORE_TPC - 1) / KP_SCORE_TPC;
     for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
@@ -170,24 +198,37 @@ __global__ void __launch_bounds__(KP_SCORE_NT) kp_score_kernel(const KpScorePara
             // two patterns per iteration: enough ILP for the FP64 pipe, small enough for the instruction cache
 #pragma unroll 1
             for (int h = 0; h < NG * 2; h++) {
+                C Mx[2], Ux[2], Mtx[2], Utx[2];
+                // counts of the two patterns: subset sums with compile-time masks, selected by a uniform switch
+#define KP_PAIR(H)                                                                                          \
+    case H:                                                                                                 \
+        Mx[0] = kp_sum_bases<kp_bm_c<R0>(2 * H), NB, C>(m); Ux[0] = kp_sum_bases<kp_bm_c<R0>(2 * H), NB, C>(u);          \
+        Mx[1] = kp_sum_bases<kp_bm_c<R0>(2 * H + 1), NB, C>(m); Ux[1] = kp_sum_bases<kp_bm_c<R0>(2 * H + 1), NB, C>(u);  \
+        if (CV) {                                                                                           \
+            Mtx[0] = kp_sum_bases<kp_bm_c<R0>(2 * H), NB, C>(mt); Utx[0] = kp_sum_bases<kp_bm_c<R0>(2 * H), NB, C>(ut);  \
+            Mtx[1] = kp_sum_bases<kp_bm_c<R0>(2 * H + 1), NB, C>(mt); Utx[1] = kp_sum_bases<kp_bm_c<R0>(2 * H + 1), NB, C>(ut); \
+        }                                                                                                   \
+        break;
+                Mtx[0] = Mtx[1] = Utx[0] = Utx[1] = 0;
+                switch (h) {
+                    KP_PAIR(0) KP_PAIR(1) KP_PAIR(2) KP_PAIR(3) KP_PAIR(4) KP_PAIR(5) KP_PAIR(6)
+                default:
+                    KP_PAIR(7)
+                }
+#undef KP_PAIR
                 float sf[2], tf[2];
 #pragma unroll
                 for (int c = 0; c < 2; c++) {
                     const int d = 2 * h + c;
                     sf[c] = 0.f; tf[c] = 0.f;
                     if (d < R0) {
-                        const unsigned bm = kp_bm<R0>(d);
-                        C M_ = 0, U_ = 0, Mt_ = 0, Ut_ = 0;
-#pragma unroll
-                        for (int b = 0; b < NB; b++)
-                            if ((bm >> b) & 1u) { M_ += m[b]; U_ += u[b]; if (CV) { Mt_ += mt[b]; Ut_ += ut[b]; } }
                         double s_, t_ = 0.0, lp_, l1_;
                         if (leafrow && d < NB) {
-                            if (!CV) s_ = kp_leaf_score_nl(M_, U_, alpha, beta, penalty, logtab);
-                            else kp_leaf_cv_nl(M_, U_, Mt_, Ut_, alpha, beta, penalty, logtab, &s_, &t_);
+                            if (!CV) s_ = kp_leaf_score_nl(Mx[c], Ux[c], alpha, beta, penalty, logtab);
+                            else kp_leaf_cv_nl(Mx[c], Ux[c], Mtx[c], Utx[c], alpha, beta, penalty, logtab, &s_, &t_);
                         } else {
-                            s_ = kp_self_score_t<C>(M_, U_, alpha, beta, penalty, logtab, lp_, l1_);
-                            if (CV) t_ = kp_test_ll((unsigned long long)Mt_, (unsigned long long)Ut_, lp_, l1_);
+                            s_ = kp_self_score_t<C>(Mx[c], Ux[c], alpha, beta, penalty, logtab, K, lp_, l1_);
+                            if (CV) t_ = kp_test_ll_t<C>(Mtx[c], Utx[c], lp_, l1_);
                         }
                         sf[c] = __double2float_rn(s_);
                         if ((double)sf[c] > s_) rupm |= 1u << d;

@@ -23,69 +23,104 @@ __constant__ double kpc_logTab[256] = KP_LOG_TAB_INIT;  // {invc, logc} x 128; C
 #define KP_SUB(a, b) __dsub_rn((a), (b))
 #define KP_MUL(a, b) __dmul_rn((a), (b))
 
+// Coefficients that enter an fma next to another constant: an fma takes one constant-bank operand for
+// free, the second one costs a load.  Pinning these few in registers (the empty asm hides them from
+// rematerialisation) removes ~12 constant loads per scored pattern.
+struct KpLogK { double a1, a3, b1, b4, b7; };
+__device__ __forceinline__ KpLogK kp_logk_load()
+{
+    KpLogK k;
+    k.a1 = kpc_logA[1]; k.a3 = kpc_logA[3]; k.b1 = kpc_logB[1]; k.b4 = kpc_logB[4]; k.b7 = kpc_logB[7];
+    asm volatile("" : "+d"(k.a1), "+d"(k.a3), "+d"(k.b1), "+d"(k.b4), "+d"(k.b7));
+    return k;
+}
+
+// window tests on the high word (the window bounds have zero low words, so this is exact)
+__device__ __forceinline__ bool kp_log_is_near1(int hi) { return (unsigned)(hi - 0x3fee0000) < 0x00030900u; }
+__device__ __forceinline__ bool kp_log_is_plain(int hi) { return (((unsigned)hi >> 16) - 0x10u) <= 0x7fdfu; }  // +normal finite
+
+// 1 - 2^-4 <= x < 1 + 0x1.09p-4, x != 1: polynomial in r = x - 1 with a split hi/lo head
+__device__ __forceinline__ double kp_log_near1(double x, const KpLogK &K)
+{
+    const double *B = kpc_logB;
+    double r = KP_SUB(x, 1.0);
+    double r2 = KP_MUL(r, r);
+    double r3 = KP_MUL(r, r2);
+    double t2 = KP_FMA(r, B[2], K.b1);
+    double t3 = KP_FMA(r, B[5], K.b4);
+    double t5 = KP_FMA(r, B[8], K.b7);
+    t2 = KP_FMA(r2, B[3], t2);
+    t3 = KP_FMA(r2, B[6], t3);
+    double t1 = KP_FMA(r2, B[9], t5);
+    t1 = KP_FMA(r3, B[10], t1);
+    t1 = KP_FMA(t1, r3, t3);
+    t1 = KP_FMA(t1, r3, t2);
+    double rw = KP_FMA(r, 0x1p27, r);
+    double rhi = KP_FMA(-0x1p27, r, rw);
+    double rlo = KP_SUB(r, rhi);
+    double rhi2 = KP_MUL(rhi, rhi);
+    double hi = KP_FMA(rhi2, -0.5, r);       // B[0] == -0.5 exactly
+    double t8 = KP_SUB(r, hi);
+    double rr = KP_ADD(r, rhi);
+    double lo = KP_FMA(rhi2, -0.5, t8);
+    double t = KP_MUL(-0.5, rlo);
+    lo = KP_FMA(t, rr, lo);
+    double y = KP_FMA(t1, r3, lo);
+    return KP_ADD(hi, y);
+}
+
+// positive, normal, finite x outside the near-1 window; (hi, lo) are the words of x
+__device__ __forceinline__ double kp_log_main(int hi, int lo, const double2 *__restrict__ tab, const KpLogK &K)
+{
+    const double *A = kpc_logA;
+    unsigned thi = (unsigned)hi - 0x3fe60000u;            // high word of ix - OFF (OFF has a zero low word)
+    int i = (int)((thi >> 13) & 127u);
+    int k = (int)thi >> 20;
+    double z = __hiloint2double(hi - (int)(thi & 0xfff00000u), lo);
+    double2 e = tab[i];  // invc, logc
+    double kd = (double)k;
+    double w = KP_FMA(kd, KP_LOG_LN2HI, e.y);
+    double r = KP_FMA(z, e.x, -1.0);
+    double q5 = KP_FMA(r, A[2], K.a1);
+    double hi_ = KP_ADD(r, w);
+    double r2 = KP_MUL(r, r);
+    double lo_ = KP_SUB(w, hi_);
+    lo_ = KP_ADD(lo_, r);
+    lo_ = KP_FMA(kd, KP_LOG_LN2LO, lo_);
+    double r3 = KP_MUL(r, r2);
+    double q1 = KP_FMA(r, A[4], K.a3);
+    lo_ = KP_FMA(r2, A[0], lo_);
+    q1 = KP_FMA(q1, r2, q5);
+    double y = KP_FMA(r3, q1, lo_);
+    return KP_ADD(y, hi_);
+}
+
 // tab: 128 x {invc, logc}, in shared memory (data-dependent index; constant memory would serialise)
 __device__ __forceinline__ double kp_log(double x, const double2 *__restrict__ tab)
 {
-    unsigned long long ix = (unsigned long long)__double_as_longlong(x);
-    unsigned top = (unsigned)(ix >> 48);
-    if (ix - 0x3fee000000000000ULL < 0x0003090000000000ULL) {
-        if (ix == 0x3ff0000000000000ULL) return 0.0;
-        const double *B = kpc_logB;
-        double r = KP_SUB(x, 1.0);
-        double r2 = KP_MUL(r, r);
-        double r3 = KP_MUL(r, r2);
-        double t2 = KP_FMA(r, B[2], B[1]);
-        double t3 = KP_FMA(r, B[5], B[4]);
-        double t5 = KP_FMA(r, B[8], B[7]);
-        t2 = KP_FMA(r2, B[3], t2);
-        t3 = KP_FMA(r2, B[6], t3);
-        double t1 = KP_FMA(r2, B[9], t5);
-        t1 = KP_FMA(r3, B[10], t1);
-        t1 = KP_FMA(t1, r3, t3);
-        t1 = KP_FMA(t1, r3, t2);
-        double rw = KP_FMA(r, 0x1p27, r);
-        double rhi = KP_FMA(-0x1p27, r, rw);
-        double rlo = KP_SUB(r, rhi);
-        double rhi2 = KP_MUL(rhi, rhi);
-        double hi = KP_FMA(rhi2, B[0], r);
-        double t8 = KP_SUB(r, hi);
-        double rr = KP_ADD(r, rhi);
-        double lo = KP_FMA(rhi2, B[0], t8);
-        double t = KP_MUL(B[0], rlo);
-        lo = KP_FMA(t, rr, lo);
-        double y = KP_FMA(t1, r3, lo);
-        return KP_ADD(hi, y);
+    KpLogK K;
+    K.a1 = kpc_logA[1]; K.a3 = kpc_logA[3]; K.b1 = kpc_logB[1]; K.b4 = kpc_logB[4]; K.b7 = kpc_logB[7];
+    int hi = __double2hiint(x), lo = __double2loint(x);
+    if (kp_log_is_near1(hi)) {
+        if (hi == 0x3ff00000 && lo == 0) return 0.0;
+        return kp_log_near1(x, K);
     }
-    if ((unsigned)(top - 0x10u) > 0x7fdfu) {
+    if (!kp_log_is_plain(hi)) {
+        unsigned long long ix = (unsigned long long)__double_as_longlong(x);
+        unsigned top = (unsigned)(ix >> 48);
         if (ix * 2 == 0) return -__longlong_as_double(0x7ff0000000000000LL);  // log(0) = -inf
         if (ix == 0x7ff0000000000000ULL) return x;
         if ((top & 0x8000u) || (top & 0x7ff0u) == 0x7ff0u) return __longlong_as_double(0x7ff8000000000000LL);
-        ix = (unsigned long long)__double_as_longlong(KP_MUL(x, 0x1p52));
+        ix = (unsigned long long)__double_as_longlong(KP_MUL(x, 0x1p52));   // subnormal
         ix -= 52ULL << 52;
+        hi = (int)(ix >> 32);
+        lo = (int)(unsigned)ix;
     }
-    unsigned long long tmp = ix - 0x3fe6000000000000ULL;
-    int i = (int)((tmp >> 45) & 127);
-    int k = (int)((long long)tmp >> 52);
-    unsigned long long iz = ix - (tmp & 0xfff0000000000000ULL);
-    double2 e = tab[i];  // invc, logc
-    double z = __longlong_as_double((long long)iz);
-    double kd = (double)k;
-    const double *A = kpc_logA;
-    double w = KP_FMA(kd, KP_LOG_LN2HI, e.y);
-    double r = KP_FMA(z, e.x, -1.0);
-    double q5 = KP_FMA(r, A[2], A[1]);
-    double hi = KP_ADD(r, w);
-    double r2 = KP_MUL(r, r);
-    double lo = KP_SUB(w, hi);
-    lo = KP_ADD(lo, r);
-    lo = KP_FMA(kd, KP_LOG_LN2LO, lo);
-    double r3 = KP_MUL(r, r2);
-    double q1 = KP_FMA(r, A[4], A[3]);
-    lo = KP_FMA(r2, A[0], lo);
-    q1 = KP_FMA(q1, r2, q5);
-    double y = KP_FMA(r3, q1, lo);
-    return KP_ADD(y, hi);
+    return kp_log_main(hi, lo, tab, K);
 }
+
+// out-of-line copy for the rare arguments the scoring kernel does not handle inline
+__device__ __noinline__ double kp_log_slow(double x, const double2 *tab) { return kp_log(x, tab); }
 
 // cephes log1p (scipy.special): log(1+x) by a 6/6 rational on [sqrt(1/2)-1, sqrt(2)-1], no fused ops
 __device__ __forceinline__ double kp_log1p(double x, const double2 *__restrict__ tab)
