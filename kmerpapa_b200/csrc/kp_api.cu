@@ -272,6 +272,7 @@ static int launch_score(kp_plan *p, bool cv, bool wide, const KpScoreParams &prm
 static int launch_dp(kp_plan *p, bool cv, KpDpParams prm, cudaStream_t st)
 {
     int nw = p->nwarps;
+    if (cv && nw > KP_MAX_WARPS_CV) nw = KP_MAX_WARPS_CV;
     if (nw < 1) return fail("DP kernel does not fit in shared memory for this tile shape");
     size_t nhl = p->host.hl_off.size() - 1;
     const KpTables &t = p->host.t;

@@ -31,7 +31,8 @@
 #include "kp_math.cuh"
 #include "kp_tables.h"
 
-#define KP_MAX_WARPS 14
+#define KP_MAX_WARPS 14      // single DP: tiles in flight per SM (<= 128 registers per thread)
+#define KP_MAX_WARPS_CV 12   // CV job: fewer warps, up to 168 registers per thread (winner codes + held-out values)
 #define KP_SCORE_NT 256     // threads per CTA of the scoring kernel
 #define KP_SCORE_TPC 8      // tiles per chunk of the scoring kernel
 
@@ -261,8 +262,11 @@ struct KpDpParams {
     uint16_t *flags;    // single: per row, bit d set = pattern kept whole
 };
 
+// CV winner code: (scan rank = position*8 + j) << 8 | where.  where = index into the tile's high-split list,
+// 0x80 | index into the row's cross-row list, or 0xFF for an in-register split (its held-out loss is at hand).
+// Codes order like scan ranks, so (value, code) compared lexicographically picks the reference's winner.
 #define KP_NONE 0x7fffffff
-#define KP_FETCH 0x40000000  // CV: winner comes from a streamed or cross-row split; held-out value still to fetch
+#define KP_INROW 0xFF
 
 template <int R0, bool CV>
 struct KpRow {
@@ -271,7 +275,7 @@ struct KpRow {
     float sv[NG * 4];            // self-score (RN_f32)
     float tv[CV ? NG * 4 : 1];   // CV: held-out loss of the current winner
     float ts[CV ? NG * 4 : 1];   // CV: held-out loss of the unsplit pattern
-    int rk[CV ? NG * 4 : 1];     // CV: scan rank of the current winner (pos*8+j), KP_NONE = none yet
+    int rk[CV ? NG * 4 : 1];     // CV: code of the current winner, KP_NONE = none yet
     uint32_t rup, flag;
 };
 
@@ -286,15 +290,15 @@ struct KpRowOps {
         if (!CV) {
             r.v[D] = fminf(r.v[D], cand);
         } else {
-            int rank = rankbase + J;
-            bool take = (cand < r.v[D]) || (cand == r.v[D] && rank < (r.rk[D] & ~KP_FETCH));
-            if (take) { r.v[D] = cand; r.rk[D] = rank; r.tv[D] = __fadd_rn(r.tv[A], r.tv[B]); }
+            int code = ((rankbase + J) << 8) | KP_INROW;
+            bool take = (cand < r.v[D]) || (cand == r.v[D] && code < r.rk[D]);
+            if (take) { r.v[D] = cand; r.rk[D] = code; r.tv[D] = __fadd_rn(r.tv[A], r.tv[B]); }
         }
     }
 };
 
 template <int R0, bool CV>
-__global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const KpDpParams p)
+__global__ void __launch_bounds__((CV ? KP_MAX_WARPS_CV : KP_MAX_WARPS) * 32, 1) kp_dp_rows_kernel(const KpDpParams p)
 {
     typedef KpRow<R0, CV> Row;
     typedef KpRowOps<R0, CV> Ops;
@@ -379,7 +383,7 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
     }
 #define KP_HS_USE(s, xa, xb)                                                                         \
     {                                                                                                \
-        const int rank = CV ? (int)hsr[s] : 0;                                                       \
+        const int code = CV ? (((int)hsr[s] << 8) | (s)) : 0;                                        \
         _Pragma("unroll") for (int g = 0; g < NG; g++) {                                             \
             float c0 = __fadd_rn(xa[g].x, xb[g].x), c1 = __fadd_rn(xa[g].y, xb[g].y);                \
             float c2 = __fadd_rn(xa[g].z, xb[g].z), c3 = __fadd_rn(xa[g].w, xb[g].w);                \
@@ -389,10 +393,10 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
                 r.v[4 * g + 2] = fminf(r.v[4 * g + 2], c2);                                          \
                 r.v[4 * g + 3] = fminf(r.v[4 * g + 3], c3);                                          \
             } else { /* hs is in scan order: a strict '<' keeps the earliest split among equals */   \
-                if (c0 < r.v[4 * g + 0]) { r.v[4 * g + 0] = c0; r.rk[4 * g + 0] = rank | KP_FETCH; } \
-                if (c1 < r.v[4 * g + 1]) { r.v[4 * g + 1] = c1; r.rk[4 * g + 1] = rank | KP_FETCH; } \
-                if (c2 < r.v[4 * g + 2]) { r.v[4 * g + 2] = c2; r.rk[4 * g + 2] = rank | KP_FETCH; } \
-                if (c3 < r.v[4 * g + 3]) { r.v[4 * g + 3] = c3; r.rk[4 * g + 3] = rank | KP_FETCH; } \
+                if (c0 < r.v[4 * g + 0]) { r.v[4 * g + 0] = c0; r.rk[4 * g + 0] = code; }           \
+                if (c1 < r.v[4 * g + 1]) { r.v[4 * g + 1] = c1; r.rk[4 * g + 1] = code; }           \
+                if (c2 < r.v[4 * g + 2]) { r.v[4 * g + 2] = c2; r.rk[4 * g + 2] = code; }           \
+                if (c3 < r.v[4 * g + 3]) { r.v[4 * g + 3] = c3; r.rk[4 * g + 3] = code; }           \
             }                                                                                        \
         }                                                                                            \
     }
@@ -455,7 +459,7 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
                 for (int i = xs_off[srow]; i < xs_off[srow + 1]; i++) {
                     const uint32_t pr = xs[i];
                     const float4 *a = S + (pr & 0xFFFFu), *b = S + (pr >> 16);
-                    const int rank = CV ? (int)xsr[i] : 0;
+                    const int code = CV ? (((int)xsr[i] << 8) | 0x80 | (i - xs_off[srow])) : 0;
 #pragma unroll
                     for (int g = 0; g < NG; g++) {
                         float4 xa = a[g * rp], xb = b[g * rp];
@@ -469,7 +473,7 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
                         } else {
                             // cross-row and streamed splits interleave in scan order: compare (value, rank)
 #define KP_CVX(c, cand)                                                                                          \
-    if ((cand) < r.v[c] || ((cand) == r.v[c] && rank < (r.rk[c] & ~KP_FETCH))) { r.v[c] = (cand); r.rk[c] = rank | KP_FETCH; }
+    if ((cand) < r.v[c] || ((cand) == r.v[c] && code < r.rk[c])) { r.v[c] = (cand); r.rk[c] = code; }
                             KP_CVX(4 * g + 0, c0) KP_CVX(4 * g + 1, c1) KP_CVX(4 * g + 2, c2) KP_CVX(4 * g + 3, c3)
 #undef KP_CVX
                         }
@@ -478,18 +482,16 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
 
                 // ---- register position: in-register splits + self-score compare, digit by digit ----
                 // CV: fetch the held-out loss of a winner that came from memory (streamed or cross-row split)
-                auto fetch_test = [&](int d, int rank) -> float {
+                auto fetch_test = [&](int d, int code) -> float {
                     const int inrow = ((d >> 2) * rp) * 4 + (d & 3);
-                    for (int i = xs_off[srow]; i < xs_off[srow + 1]; i++)
-                        if ((int)xsr[i] == rank) {
-                            const float *t0 = p.test + (size_t)tile * stride + inrow;
-                            return __fadd_rn(__ldcg(t0 + (xs[i] & 0xFFFFu) * 4), __ldcg(t0 + (xs[i] >> 16) * 4));
-                        }
-                    for (int s = 0; s < nhs; s++)
-                        if ((int)hsr[s] == rank)
-                            return __fadd_rn(__ldg(p.test + (size_t)hs1[s] * stride + inrow + srow * 4),
-                                             __ldg(p.test + (size_t)hs2[s] * stride + inrow + srow * 4));
-                    return 0.f;
+                    if (code & 0x80) {  // cross-row split: rows of this tile, written by this warp in earlier rounds
+                        const uint32_t pr = xs[xs_off[srow] + (code & 0x7F)];
+                        const float *t0 = p.test + (size_t)tile * stride + inrow;
+                        return __fadd_rn(__ldcg(t0 + (pr & 0xFFFFu) * 4), __ldcg(t0 + (pr >> 16) * 4));
+                    }
+                    const int s = code & 0x7F;  // high-position split: the two child tiles, same row
+                    return __fadd_rn(__ldg(p.test + (size_t)hs1[s] * stride + inrow + srow * 4),
+                                     __ldg(p.test + (size_t)hs2[s] * stride + inrow + srow * 4));
                 };
                 // reference: if s < (double)best: best = f32(s)   <=>   sf < best || (sf == best && sf > s)
 #define KP_FIN(D)                                                                                                \
@@ -499,7 +501,7 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
             if (self_) { r.v[D] = r.sv[D]; r.flag |= 1u << (D); }                                                \
         } else {                                                                                                 \
             if (self_) { r.v[D] = r.sv[D]; r.tv[D] = r.ts[D]; }                                                  \
-            else if (r.rk[D] & KP_FETCH) r.tv[D] = fetch_test(D, r.rk[D] & ~KP_FETCH);                           \
+            else if ((r.rk[D] & 0xFF) != KP_INROW) r.tv[D] = fetch_test(D, r.rk[D]);                             \
         }                                                                                                        \
     }
 #define KP_SP(D, A, B, J) Ops::template split<D, A, B, J>(r, rankbase);
