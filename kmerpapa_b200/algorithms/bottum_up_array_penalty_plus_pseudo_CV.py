@@ -90,7 +90,9 @@ def select_best(alphas, penalties, results, nit, nfolds, k, cvfile=None):
             test = fold_sum(vals, nit)
             if cvfile is not None:
                 print(k, alpha, penalty, test, file=cvfile)
-            if test < best_test_loss:
+            with np.errstate(over="ignore"):   # float32 test against the 1e100 start value, as in the reference
+                better = test < best_test_loss
+            if better:
                 best_values = (alpha, penalty)
                 best_test_loss = test
     return best_values[0], best_values[1], best_test_loss

@@ -169,9 +169,12 @@ def worker_cli(spec_path, out_path):
     err = io.StringIO()
     with contextlib.redirect_stderr(err):
         rc = cli.main(argv)
+    import gc
+
+    gc.collect()   # cli.main leaves its output files to the garbage collector: make sure they are flushed
     res = {"argv": spec["argv"], "rc": rc, "stdout": open(out_file).read(),
            "cvfile": open(cv_file).read() if os.path.exists(cv_file) else None,
-           "stderr": [l for l in err.getvalue().splitlines() if "Warning" not in l and "np.full" not in l]}
+           "stderr": [l for l in err.getvalue().splitlines() if "Warning" not in l and not l.startswith("  ")]}
     for f in (out_file, cv_file):
         if os.path.exists(f):
             os.remove(f)

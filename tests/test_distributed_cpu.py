@@ -1,0 +1,90 @@
+"""Job sharding + gather over torch.distributed with the gloo backend, world_size 2, on CPU.
+The per-job runner is a stand-in (the CPU oracle on a small general pattern): what is under test is the
+host logic every rank runs — same fold tables, contiguous job chunks, one all_gather, identical selection."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+GEN_PAT, ALPHAS, PENS, NF, SEED = "NNN", [0.5, 2.0], [2.0, 5.0, 7.0], 3, 4
+
+
+def _data():
+    rng = np.random.default_rng(3)
+    U = 1 + rng.negative_binomial(2, 2 / (2 + 900.0), size=64)
+    M = rng.binomial(U, 0.03)
+    return M.astype(np.int64), U.astype(np.int64)
+
+
+class OracleRunner:
+    device = None
+
+    def __init__(self, gen_pat, M, U):
+        sys.path.insert(0, ROOT)
+        from oracle import kp_oracle
+
+        self.O, self.gp, self.M, self.U = kp_oracle, gen_pat, M, U
+        self.calls = 0
+
+    def set_folds(self, Mf, Uf):
+        self.Mf, self.Uf = Mf, Uf
+
+    def run(self, f, alpha, beta, penalty):
+        self.calls += 1
+        tr, te = self.O.cv_job(self.gp, self.M, self.U, self.Mf[:, f], self.Uf[:, f], alpha, beta, penalty, nthreads=1)
+        return tr[-1], te[-1]
+
+
+def _grid(rank, world):
+    from kmerpapa_b200 import iupac
+    from kmerpapa_b200.algorithms import bottum_up_array_penalty_plus_pseudo_CV as cv
+
+    M, U = _data()
+    kmers = iupac.matches(GEN_PAT)
+    runner = OracleRunner(GEN_PAT, M, U)
+    res = cv.run_grid(GEN_PAT, kmers, None, M, U, ALPHAS, PENS, NF, 1, SEED, runner=runner, gather_device=None)
+    return res, runner.calls
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res, calls = _grid(rank, world)
+    q.put((rank, res.tobytes(), calls))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_cv_grid_sharded_over_two_ranks_matches_single_process(oracle):
+    from kmerpapa_b200.algorithms import bottum_up_array_penalty_plus_pseudo_CV as cv
+
+    single, calls = _grid(0, 1)
+    njobs = NF * len(ALPHAS) * len(PENS)
+    assert calls == njobs
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, blob, c in got:
+        assert blob == single.tobytes()                      # every rank ends with the full, identical result
+        lo, hi = cv.shard_bounds(njobs, rank, 2)
+        assert c == hi - lo                                  # and only ran its own chunk
+    # selection equals the oracle's own grid driver
+    M, U = _data()
+    ref = oracle.cv_grid(GEN_PAT, M, U, ALPHAS, PENS, NF, SEED, nthreads=1)
+    a, c, best = cv.select_best(ALPHAS, PENS, single, 1, NF, len(GEN_PAT))
+    assert (a, c) == (ref["best"][0], ref["best"][1]) and np.float32(best) == np.float32(ref["best"][2])

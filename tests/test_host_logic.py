@@ -1,0 +1,167 @@
+"""CPU tests of the host side: IUPAC tables, input parsing, fold sampler, CV reduction, job sharding,
+the C ABI surface.  No GPU needed."""
+import ctypes
+import io
+import json
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, golden_files
+
+
+def test_iupac_tables_against_oracle(oracle):
+    from kmerpapa_b200 import iupac
+
+    for gp in ("NNMNN", "SWSW", "RYNBA", "NAA"):
+        npat, nk, lvl = oracle.plan_info(gp)
+        PE = iupac.PatternEnumeration(gp)
+        assert PE.npat == npat == iupac.pattern_max(gp)
+        assert iupac.pattern_level(gp) == lvl
+        assert iupac.matches(gp) == oracle.kmers_of(gp) and len(iupac.matches(gp)) == nk
+        for num in list(range(0, npat, max(1, npat // 300))) + [npat - 1]:
+            pat = oracle.num2pattern(gp, num)
+            assert PE.num2pattern(num) == pat and PE.pattern2num(pat) == num
+        assert iupac.lca_pattern(iupac.matches(gp)) == gp
+    assert iupac.contains("NNANN", "CGATT") and not iupac.contains("NNANN", "CGCTT")
+    assert iupac.kmer_code("ACGT") == 1 | 2 << 4 | 4 << 8 | 8 << 12
+
+
+def test_read_input_test_data():
+    from kmerpapa_b200 import io_utils
+
+    args = types.SimpleNamespace(positive=open(f"{GOLDEN}/data/mutated_5mers.txt"), negative=None,
+                                 background=open(f"{GOLDEN}/data/background_5mers.txt"), joint_context_counts=None)
+    table, n_unmut, n_mut = io_utils.read_input(args, None)
+    assert (n_mut, n_unmut) == (59479, 2164774234)           # the reference's "Input data read." line (cfg 1)
+    assert len(table) == 512 and all(u >= 0 for _, u in table.values())
+    args = types.SimpleNamespace(positive=open(f"{GOLDEN}/data/mutated_5mers.txt"), negative=None,
+                                 background=open(f"{GOLDEN}/data/background_7mers.txt"), joint_context_counts=None)
+    t2, u2, m2 = io_utils.read_input(args, "RNAYN")           # longer background k-mers are centre-trimmed
+    assert all(len(k) == 5 and k[0] in "AG" and k[2] == "A" and k[3] in "CT" for k in t2)
+
+
+def test_read_dict_rules():
+    from kmerpapa_b200 import io_utils
+
+    f = io.StringIO("ACGTA 3\nACNTA 9\nACGTA 2.0\nTTTTT 1e1\n")
+    table, total = io_utils.read_dict(f, None)
+    assert table == {"ACGTA": 5, "TTTTT": 10} and total == 15     # N skipped, duplicates add, float counts
+    f = io.StringIO("AACGTAA 4\nCACGTAC 1\n")
+    table, total = io_utils.read_dict(f, None, length=5)
+    assert table == {"ACGTA": 5} and total == 5
+    with pytest.raises(AssertionError):
+        io_utils.read_dict(io.StringIO("ACG -1\n"), None)
+    joint, n_unmut, n_mut = io_utils.read_joint_kmer_counts(io.StringIO("ACG 2 10\nACT 0 5\n"), None)
+    assert joint == {"ACG": (2, 8), "ACT": (0, 5)} and (n_unmut, n_mut) == (13, 2)
+    small, gp = io_utils.downsize_contextD({"AACGT": (1, 2), "CACGA": (3, 4)}, "NNCGN", 3)
+    assert small == {"ACG": [4, 6]} and gp == "NCG"
+
+
+@pytest.mark.parametrize("path", golden_files("cv"), ids=lambda p: p.split("cv_")[-1][:-4])
+def test_fold_sampler_matches_reference_stream(oracle, path):
+    """Same numpy RandomState stream as the reference's CV_tools (held-out counts per fold)."""
+    from kmerpapa_b200 import CV_tools, iupac
+
+    g = np.load(path)
+    gp, nf = str(g["gen_pat"]), int(g["nfolds"])
+    kmers = iupac.matches(gp)
+    Mf, Uf = CV_tools.sample_fold_counts(kmers, g["kmerM"], g["kmerU"], nf, np.random.RandomState(int(g["seed"])))
+    pn = oracle.kmer_patnums(gp).astype(np.int64)
+    assert np.array_equal(Mf, g["M_folds"][pn]) and np.array_equal(Uf, g["U_folds"][pn])
+    # a shuffled input order must give the same table (the sampler sorts k-mers itself)
+    perm = np.random.default_rng(0).permutation(len(kmers))
+    Mf2, Uf2 = CV_tools.sample_fold_counts([kmers[i] for i in perm], g["kmerM"][perm], g["kmerU"][perm], nf,
+                                           np.random.RandomState(int(g["seed"])))
+    assert np.array_equal(Mf2, Mf[perm]) and np.array_equal(Uf2, Uf[perm])
+
+
+def test_fold_sums_like_reference_test():
+    """tests/test_CV_tools.py of the reference: folds add back to the table."""
+    from kmerpapa_b200 import CV_tools
+
+    kmers = ["AAA", "CAA", "GAA", "TAA"]
+    pos, neg = np.array([10, 200, 500, 300]), np.array([100, 1000, 2000, 1000])
+    Mf, Uf = CV_tools.sample_fold_counts(kmers, pos, neg, 10, np.random.RandomState(0))
+    assert Mf.shape == (4, 10) and np.array_equal(Mf.sum(axis=1), pos) and np.array_equal(Uf.sum(axis=1), neg)
+
+
+def test_cv_reduction_and_selection_format():
+    """float32 sequential fold sum, strict '<' selection alpha-outer / penalty-inner, CVfile row text."""
+    from kmerpapa_b200.algorithms import bottum_up_array_penalty_plus_pseudo_CV as cv
+
+    res = np.zeros((1, 2, 2, 2, 2), dtype=np.float32)
+    res[0, :, 0, 0, 1] = [662892.56, 662892.56]
+    res[0, :, 0, 1, 1] = [662838.5, 662838.5]
+    res[0, :, 1, 0, 1] = [662838.5, 662838.5]       # tie with the earlier grid point: the earlier one stays
+    res[0, :, 1, 1, 1] = [662900.0, 662900.0]
+    out = io.StringIO()
+    a, c, best = cv.select_best([0.8, 1.0], [3.0, 5.0], res, 1, 2, 5, out)
+    assert (a, c) == (0.8, 5.0) and isinstance(best, np.float32) and best == np.float32(1325677.0)
+    assert out.getvalue().splitlines()[1] == "5 0.8 5.0 1.325677e+06"
+    assert cv.fold_sum([np.float32(16777216.0), np.float32(1.0), np.float32(1.0)], 1) == np.float32(16777216.0)  # f32 accumulation
+
+
+def test_job_sharding():
+    from kmerpapa_b200.algorithms import bottum_up_array_penalty_plus_pseudo_CV as cv
+
+    jobs = cv.job_list(1, 5, 3, 3)
+    assert len(jobs) == 45 and jobs[0] == (0, 0, 0, 0) and jobs[9] == (0, 1, 0, 0)
+    for world in (1, 2, 4, 8, 45, 64):
+        covered = []
+        for r in range(world):
+            lo, hi = cv.shard_bounds(45, r, world)
+            covered += list(range(lo, hi))
+            folds = {jobs[j][1] for j in range(lo, hi)}
+            if world <= 8:
+                assert len(folds) <= 2 + (45 // world) // 9
+        assert covered == list(range(45))
+    assert cv.covering_patterns_per_kmer("NNMNA") == 8 * 8 * 2 * 8
+
+
+def test_cli_smoke(capsys):
+    """The reference's own CLI tests: no input -> help + 'input error', exit code 0; -h exits."""
+    from kmerpapa_b200 import cli
+
+    assert cli.main([]) == 0
+    with pytest.raises(SystemExit):
+        cli.main(["-h"])
+    assert "kmerpapa" in capsys.readouterr().out
+    p = cli.get_parser().parse_args(["--n_folds", "5", "-c", "3", "5"])
+    assert p.nfolds == 5 and p.penalty_values == [3.0, 5.0] and p.pseudo_counts == [0.8]
+    assert cli.get_parser().parse_args(["--nfolds", "3"]).nfolds == 3
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """libkpapa.so loads and exports exactly what include/kmerpapa_b200.h declares (no compute calls)."""
+    from kmerpapa_b200 import _native, build
+
+    build.build_native()
+    header = open(os.path.join(ROOT, "include", "kmerpapa_b200.h")).read()
+    declared = set(re.findall(r"\b(kp_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    L = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in the header but not exported"
+    assert declared == set(_native.SYMBOLS), "ctypes table and header disagree"
+    assert _native.lib().kp_version() >= 100
+    assert ctypes.sizeof(_native.PlanInfo) == 7 * 8 + 12 * 4
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a CUDA device the product path raises; it never routes to the oracle."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from kmerpapa_b200._native import KpError
+    from kmerpapa_b200.engine import get_plan
+
+    with pytest.raises(KpError):
+        get_plan("NNN")
+    src = "".join(open(os.path.join(dp, f)).read() for dp, _, fs in os.walk(os.path.join(ROOT, "kmerpapa_b200"))
+                  for f in fs if f.endswith(".py"))
+    assert "oracle" not in src.replace("no CPU", ""), "product code must not reference the oracle"
