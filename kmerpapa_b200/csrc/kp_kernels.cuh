@@ -371,6 +371,11 @@ __global__ void __launch_bounds__((CV ? KP_MAX_WARPS_CV : KP_MAX_WARPS) * 32, 1)
         const float *tbase = p.best;
         float4 *otile = (float4 *)(p.best + (size_t)tile * stride);
         const float4 *stile = (const float4 *)(p.self + (size_t)tile * stride);
+        // the tile's self-scores are consumed round by round later on: pull them into L2 now
+        for (uint32_t off = lane * 32u; off < stride; off += 32u * 32u) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.self + (size_t)tile * stride + off));
+            if (CV) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.tself + (size_t)tile * stride + off));
+        }
 
         // ---- phase D (single DP): stream the child tiles of the high-position splits for ALL rows of the tile,
         //      32 consecutive rows at a time, two splits in flight; the running minimum of row r is parked
@@ -414,15 +419,58 @@ __global__ void __launch_bounds__((CV ? KP_MAX_WARPS_CV : KP_MAX_WARPS) * 32, 1)
         if (s < nhs) KP_HS_USE(s, xa0, xb0)                                                          \
     }
         if (!CV) {
-            for (int srow = lane; srow < tb.nrows; srow += 32) {
-                Row r;
+            // one flattened software pipeline over (32-row chunk, split): a load is always two steps ahead of
+            // its use, also across chunk boundaries, so the pipeline drains once per tile, not once per chunk
+            Row r;
 #pragma unroll
-                for (int c = 0; c < NG * 4; c++) r.v[c] = INF;
-                KP_HS_STREAM()
-#pragma unroll
-                for (int g = 0; g < NG; g++)
-                    S[g * rp + srow] = make_float4(r.v[4 * g], r.v[4 * g + 1], r.v[4 * g + 2], r.v[4 * g + 3]);
+            for (int c = 0; c < NG * 4; c++) r.v[c] = INF;
+            const int nrows = tb.nrows;
+            const int nchunk = (nrows + 31) >> 5;
+            const int nstep = nhs > 0 ? nchunk * nhs : 0;
+            float4 xa0[NG], xb0[NG], xa1[NG], xb1[NG];
+            int ls = 0, lrow = lane;          // split and row of the next load
+            int us = 0, urow = lane;          // split and row of the next use
+#define KP_FL_LOAD(xa, xb)                                                                            \
+    {                                                                                                 \
+        const int row_ = lrow < nrows ? lrow : nrows - 1;   /* idle lanes of the last chunk re-read a valid row */ \
+        const float4 *a_ = (const float4 *)(tbase + (size_t)hs1[ls] * stride) + row_;                 \
+        const float4 *b_ = (const float4 *)(tbase + (size_t)hs2[ls] * stride) + row_;                 \
+        _Pragma("unroll") for (int g = 0; g < NG; g++) { xa[g] = __ldg(a_ + g * rp); xb[g] = __ldg(b_ + g * rp); } \
+        if (++ls == nhs) { ls = 0; lrow += 32; }                                                      \
+    }
+#define KP_FL_USE(xa, xb)                                                                             \
+    {                                                                                                 \
+        _Pragma("unroll") for (int g = 0; g < NG; g++) {                                              \
+            r.v[4 * g + 0] = fminf(r.v[4 * g + 0], __fadd_rn(xa[g].x, xb[g].x));                      \
+            r.v[4 * g + 1] = fminf(r.v[4 * g + 1], __fadd_rn(xa[g].y, xb[g].y));                      \
+            r.v[4 * g + 2] = fminf(r.v[4 * g + 2], __fadd_rn(xa[g].z, xb[g].z));                      \
+            r.v[4 * g + 3] = fminf(r.v[4 * g + 3], __fadd_rn(xa[g].w, xb[g].w));                      \
+        }                                                                                             \
+        if (++us == nhs) {   /* chunk complete: park its minima, start the next chunk */              \
+            if (urow < nrows) {                                                                       \
+                _Pragma("unroll") for (int g = 0; g < NG; g++)                                        \
+                    S[g * rp + urow] = make_float4(r.v[4 * g], r.v[4 * g + 1], r.v[4 * g + 2], r.v[4 * g + 3]); \
+            }                                                                                         \
+            _Pragma("unroll") for (int c = 0; c < NG * 4; c++) r.v[c] = INF;                          \
+            us = 0; urow += 32;                                                                       \
+        }                                                                                             \
+    }
+            if (nstep > 0) KP_FL_LOAD(xa0, xb0)
+            int t = 0;
+            for (; t + 2 <= nstep; t += 2) {
+                KP_FL_LOAD(xa1, xb1)
+                KP_FL_USE(xa0, xb0)
+                if (t + 2 < nstep) KP_FL_LOAD(xa0, xb0)
+                KP_FL_USE(xa1, xb1)
             }
+            if (t < nstep) KP_FL_USE(xa0, xb0)
+#undef KP_FL_LOAD
+#undef KP_FL_USE
+            if (nstep == 0)  // no high-position split (wave 0, or a pattern without high positions)
+                for (int srow = lane; srow < nrows; srow += 32) {
+#pragma unroll
+                    for (int g = 0; g < NG; g++) S[g * rp + srow] = make_float4(INF, INF, INF, INF);
+                }
             __syncwarp();
         }
 
