@@ -45,38 +45,56 @@ def measured_peak():
 
 
 class ClockSampler:
-    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks and throttle reasons through NVML (in-process thread) while the timed region runs.
+    NVML is initialised in __init__, well before the timed region: spawning nvidia-smi or initialising NVML
+    next to the timed steps stalls the driver for tens of milliseconds and would distort the measurement."""
 
-    def __init__(self, index):
-        self.rows, self.stop_flag, self.index = [], False, index
-        self.proc = None
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
+    def __init__(self, index, period_s=0.1):
+        self.rows, self.period, self.running, self.thread = [], period_s, False, None
+        self.handle = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # NVML missing: report it, do not guess
+            self.error = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while self.running:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append((float(mhz), int(rs)))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        if self.handle is None:
+            return
+        self.running = True
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.handle is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "error", "?")]}
+        self.running = False
         self.thread.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({name for _, bits in self.rows for name, bit in self.REASONS.items() if bits & bit})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
                 "samples": len(sm)}
 
 
@@ -214,10 +232,10 @@ def bench_single(args, rank, world, local):
         patnums = plan.backtrack(best, kept)
         return plan.top_score(best), patnums
 
+    sampler = ClockSampler(local)
     for _ in range(args.warmup):
         loss, patnums = device_step()
     barrier_sync(world)
-    sampler = ClockSampler(local)
     sampler.start()
     l0 = plan.launches
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -258,9 +276,9 @@ def bench_single(args, rank, world, local):
                    "loss": float(loss), "l2": "score+split tables 12.9 GB >> 126 MB L2, no flush needed",
                    "replicas": world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": load_traffic("single_dp_bytes"), "kernel": "kp_dp_wave_kernel<single>, all waves of one DP",
+                     "traffic": load_traffic("single_dp_bytes"), "kernel": "kp_score_kernel + kp_dp_rows_kernel<single>, all launches of one DP (K3+K4)",
                      "kernel_ms": dp_ms, "algorithmic_bytes_per_pattern": ALGO_BYTES_SINGLE, "peak_kind": peak_kind,
-                     "design_bytes_per_pattern": 9.0 + 8.0 * 64 * 2 / 3375},
+                     "design_bytes_per_pattern": 4.0 * 3616 / 3375 * 4 + 6 * 226 / 3375.0},
         "e2e": {"value": world * npat / (e2e_ms / 1e3), "unit": "patterns/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(codes.nbytes + pos_p.nbytes + neg_p.nbytes),
                 "d2h_bytes_per_step": int(4 + 8 * len(patnums) + 16)},
@@ -293,10 +311,10 @@ def bench_cv(args, rank, world, local, steps=None, warmup=None):
                           presampled=[folds])
         return cv.select_best(CV_ALPHAS, CV_PENALTIES, res, 1, CV_FOLDS, len(GEN_PAT))
 
+    sampler = ClockSampler(local)
     for _ in range(warmup):
         best = step()
     barrier_sync(world)
-    sampler = ClockSampler(local)
     sampler.start()
     l0 = plan.launches
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -351,7 +369,7 @@ def main():
                        "nfolds": CV_FOLDS, "l2": "train/test table 20.6 GB per job >> 126 MB L2, no flush needed"},
             "roofline": {"bound": "hbm", "achieved": cvres["achieved_gbs_per_gpu"], "peak": cvres["peak"], "unit": "GB/s",
                          "frac": cvres["frac_per_gpu"], "traffic": load_traffic("cv_job_bytes"),
-                         "kernel": "kp_dp_wave_kernel<cv>, per GPU", "algorithmic_bytes_per_pattern": ALGO_BYTES_CV,
+                         "kernel": "kp_score_kernel<cv> + kp_dp_rows_kernel<cv>, per GPU", "algorithmic_bytes_per_pattern": ALGO_BYTES_CV,
                          "peak_kind": cvres["peak_kind"]},
             "e2e": {"value": cvres["pattern_scores_per_s"], "unit": "patterns/s", "h2d_bytes_per_step": int(65536 * 8 * 3 * 6),
                     "d2h_bytes_per_step": int(8 * cvres["jobs"]),

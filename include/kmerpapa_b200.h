@@ -136,6 +136,9 @@ int kp_dp_cv_job(kp_plan *plan, const int64_t *d_expMtot, const int64_t *d_expUt
 int kp_pattern_counts(kp_plan *plan, const int64_t *d_kmerM, const int64_t *d_kmerU, const uint64_t *h_patnums,
                       uint64_t n, int64_t *h_M, int64_t *h_U, void *stream);
 
+/* Where a dense pattern number lives in the device layout: element of a float table, element and bit of d_kept. */
+int kp_pattern_offset(const kp_plan *plan, uint64_t patnum, uint64_t *table_elem, uint64_t *kept_elem, uint32_t *kept_bit);
+
 /* Number of kernel launches issued through this plan so far (for bench.py's gpu_launches). */
 uint64_t kp_plan_launch_count(const kp_plan *plan);
 

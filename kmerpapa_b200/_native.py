@@ -42,6 +42,7 @@ SYMBOLS = {
     "kp_gather_kept": (_int, [_vp, _vp, _u64, _u64, _vp, _vp]),
     "kp_dp_cv_job": (_int, [_vp, _vp, _vp, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "kp_pattern_counts": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp]),
+    "kp_pattern_offset": (_int, [_vp, _u64, ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(ctypes.c_uint32)]),
     "kp_plan_launch_count": (_u64, [_vp]),
     "kp_debug_log": (_int, [_int, _vp, _vp, _u64]),
     "kp_debug_leaf_score": (_int, [_int, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp]),

@@ -40,6 +40,8 @@ struct kp_plan {
     uint8_t *d_genmask = nullptr;
     int *d_err = nullptr;
     uint32_t *d_counters = nullptr;  // one tile counter per wave
+    unsigned char *d_scratch = nullptr;  // staging for the small host<->device exchanges (grown on demand)
+    size_t scratch_cap = 0;
     uint64_t launches = 0;
     int nwarps = 0;          // warps (= tiles in flight) per CTA of the DP kernel
     size_t smem_optin = 0;
@@ -153,11 +155,12 @@ int kp_plan_destroy(kp_plan *p)
     cudaFree(p->d_genmask);
     cudaFree(p->d_err);
     cudaFree(p->d_counters);
+    cudaFree(p->d_scratch);
     delete p;
     return 0;
 }
 
-uint64_t kp_backtrack_ws_bytes(uint64_t cap) { return (3 * cap) * sizeof(KpBtNode) + cap * 8 + 64; }
+uint64_t kp_backtrack_ws_bytes(uint64_t cap) { return (3 * cap) * sizeof(KpBtNode) + cap * 8 + 80 * 8; }
 
 int kp_plan_get_info(const kp_plan *p, kp_plan_info *o)
 {
@@ -188,6 +191,33 @@ int kp_plan_get_info(const kp_plan *p, kp_plan_info *o)
 
 uint64_t kp_plan_launch_count(const kp_plan *p) { return p ? p->launches : 0; }
 
+int kp_pattern_offset(const kp_plan *p, uint64_t patnum, uint64_t *table_elem, uint64_t *kept_elem, uint32_t *kept_bit)
+{
+    if (!p) return fail("kp_pattern_offset: null plan");
+    if (patnum >= p->host.npat) return fail("kp_pattern_offset: pattern number out of range");
+    uint64_t tile; uint32_t srow, d0;
+    kp_locate(p->host, patnum, &tile, &srow, &d0);
+    const KpTables &t = p->host.t;
+    if (table_elem) *table_elem = tile * t.tile_stride + ((uint64_t)(d0 >> 2) * t.rp + srow) * 4 + (d0 & 3);
+    if (kept_elem) *kept_elem = tile * (uint64_t)t.rp + srow;
+    if (kept_bit) *kept_bit = d0;
+    return 0;
+}
+
+// plan-owned staging buffer: no allocator traffic on the hot host paths (stream-ordered use only)
+static int scratch_reserve(kp_plan *p, size_t bytes, cudaStream_t st)
+{
+    if (bytes <= p->scratch_cap) return 0;
+    KP_CUDA(cudaStreamSynchronize(st));
+    if (p->d_scratch) KP_CUDA(cudaFree(p->d_scratch));
+    p->d_scratch = nullptr;
+    p->scratch_cap = 0;
+    size_t cap = bytes + bytes / 2 + 4096;
+    KP_CUDA(cudaMalloc(&p->d_scratch, cap));
+    p->scratch_cap = cap;
+    return 0;
+}
+
 static int grid_for(uint64_t n, int threads, int sm_count)
 {
     uint64_t b = (n + threads - 1) / threads;
@@ -207,11 +237,9 @@ int kp_pack_counts(kp_plan *p, const uint64_t *h_codes, const int64_t *h_pos, co
     KP_CUDA(cudaMemsetAsync(d_kmerM, 0, p->host.nkmer * 8, st));
     KP_CUDA(cudaMemsetAsync(d_kmerU, 0, p->host.nkmer * 8, st));
     if (n == 0) return 0;
-    unsigned long long *d_codes = nullptr;
-    long long *d_pos = nullptr, *d_neg = nullptr;
-    KP_CUDA(cudaMallocAsync(&d_codes, n * 8, st));
-    KP_CUDA(cudaMallocAsync(&d_pos, n * 8, st));
-    KP_CUDA(cudaMallocAsync(&d_neg, n * 8, st));
+    if (scratch_reserve(p, n * 24, st)) return 1;
+    unsigned long long *d_codes = (unsigned long long *)p->d_scratch;
+    long long *d_pos = (long long *)(d_codes + n), *d_neg = d_pos + n;
     KP_CUDA(cudaMemcpyAsync(d_codes, h_codes, n * 8, cudaMemcpyHostToDevice, st));
     KP_CUDA(cudaMemcpyAsync(d_pos, h_pos, n * 8, cudaMemcpyHostToDevice, st));
     KP_CUDA(cudaMemcpyAsync(d_neg, h_neg, n * 8, cudaMemcpyHostToDevice, st));
@@ -222,9 +250,6 @@ int kp_pack_counts(kp_plan *p, const uint64_t *h_codes, const int64_t *h_pos, co
     KP_CUDA(cudaGetLastError());
     int herr = 0;
     KP_CUDA(cudaMemcpyAsync(&herr, p->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
-    KP_CUDA(cudaFreeAsync(d_codes, st));
-    KP_CUDA(cudaFreeAsync(d_pos, st));
-    KP_CUDA(cudaFreeAsync(d_neg, st));
     KP_CUDA(cudaStreamSynchronize(st));
     if (herr) return fail("kp_pack_counts: a k-mer code is not one-hot or lies outside the general pattern");
     return 0;
@@ -383,18 +408,24 @@ int kp_backtrack(kp_plan *p, const float *d_best, const uint16_t *d_kept, void *
     KP_CUDA(cudaSetDevice(p->device));
     KpBtNode *fa = (KpBtNode *)d_ws, *fb = fa + cap, *leaves = fb + cap;
     unsigned long long *sorted = (unsigned long long *)(leaves + cap);
-    unsigned long long *counts = sorted + cap;
-    kp_backtrack_kernel<<<1, 256, 0, st>>>(p->d_tab, p->d_rowtab, d_best, d_kept, p->host.npat - 1, fa, fb, leaves, cap, counts);
-    p->launches++;
+    unsigned long long *ctr = sorted + cap;   // [0] leaves, [1] overflow, [2 + d] nodes at depth d
+    kp_backtrack_init_kernel<<<1, 128, 0, st>>>(fa, p->host.npat - 1, ctr);
+    const int levels = (int)p->host.t.total_level + 1;
+    int grid = (int)((cap + 7) / 8);
+    if (grid > p->sm_count * 2) grid = p->sm_count * 2;
+    for (int d = 0; d < levels && d < 64; d++) {
+        kp_backtrack_level_kernel<<<grid, 256, 0, st>>>(p->d_tab, p->d_rowtab, d_best, d_kept, d, (d & 1) ? fb : fa,
+                                                        (d & 1) ? fa : fb, leaves, cap, ctr);
+        p->launches++;
+    }
+    kp_backtrack_sort_kernel<<<p->sm_count, 256, 0, st>>>(leaves, ctr, cap, sorted);
+    p->launches += 2;
     KP_CUDA(cudaGetLastError());
     unsigned long long hc[2] = {0, 0};
-    KP_CUDA(cudaMemcpyAsync(hc, counts, sizeof hc, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaMemcpyAsync(hc, ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaStreamSynchronize(st));
     *n_out = hc[0];
     if (hc[1] || hc[0] > cap) return fail("kp_backtrack: partition larger than the workspace capacity");
-    kp_backtrack_sort_kernel<<<(int)((hc[0] + 255) / 256), 256, 0, st>>>(leaves, counts, cap, sorted);
-    p->launches++;
-    KP_CUDA(cudaGetLastError());
     KP_CUDA(cudaMemcpyAsync(h_patnums, sorted, hc[0] * 8, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaStreamSynchronize(st));
     return 0;
@@ -407,17 +438,14 @@ int kp_split_codes(kp_plan *p, const float *d_best, const uint16_t *d_kept, cons
     if (n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     KP_CUDA(cudaSetDevice(p->device));
-    unsigned long long *d_pat = nullptr;
-    uint8_t *d_codes = nullptr;
-    KP_CUDA(cudaMallocAsync(&d_pat, n * 8, st));
-    KP_CUDA(cudaMallocAsync(&d_codes, n, st));
+    if (scratch_reserve(p, n * 9, st)) return 1;
+    unsigned long long *d_pat = (unsigned long long *)p->d_scratch;
+    uint8_t *d_codes = (uint8_t *)(d_pat + n);
     KP_CUDA(cudaMemcpyAsync(d_pat, h_patnums, n * 8, cudaMemcpyHostToDevice, st));
     kp_split_codes_kernel<<<grid_for(n, 256, p->sm_count), 256, 0, st>>>(p->d_tab, p->d_rowtab, d_best, d_kept, d_pat, n, d_codes);
     p->launches++;
     KP_CUDA(cudaGetLastError());
     KP_CUDA(cudaMemcpyAsync(h_codes, d_codes, n, cudaMemcpyDeviceToHost, st));
-    KP_CUDA(cudaFreeAsync(d_pat, st));
-    KP_CUDA(cudaFreeAsync(d_codes, st));
     KP_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
@@ -428,13 +456,12 @@ int kp_gather_table(kp_plan *p, const float *d_table, uint64_t first, uint64_t n
     if (n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     KP_CUDA(cudaSetDevice(p->device));
-    float *d_out = nullptr;
-    KP_CUDA(cudaMallocAsync(&d_out, n * 4, st));
+    if (scratch_reserve(p, n * 4, st)) return 1;
+    float *d_out = (float *)p->d_scratch;
     kp_gather_kernel<<<grid_for(n, 256, p->sm_count), 256, 0, st>>>(p->d_tab, p->d_rowtab, d_table, nullptr, first, n, d_out);
     p->launches++;
     KP_CUDA(cudaGetLastError());
     KP_CUDA(cudaMemcpyAsync(h_out, d_out, n * 4, cudaMemcpyDeviceToHost, st));
-    KP_CUDA(cudaFreeAsync(d_out, st));
     KP_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
@@ -445,13 +472,12 @@ int kp_gather_kept(kp_plan *p, const uint16_t *d_kept, uint64_t first, uint64_t 
     if (n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     KP_CUDA(cudaSetDevice(p->device));
-    uint8_t *d_out = nullptr;
-    KP_CUDA(cudaMallocAsync(&d_out, n, st));
+    if (scratch_reserve(p, n, st)) return 1;
+    uint8_t *d_out = (uint8_t *)p->d_scratch;
     kp_gather_flags_kernel<<<grid_for(n, 256, p->sm_count), 256, 0, st>>>(p->d_tab, p->d_rowtab, d_kept, first, n, d_out);
     p->launches++;
     KP_CUDA(cudaGetLastError());
     KP_CUDA(cudaMemcpyAsync(h_out, d_out, n, cudaMemcpyDeviceToHost, st));
-    KP_CUDA(cudaFreeAsync(d_out, st));
     KP_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
@@ -463,10 +489,9 @@ int kp_pattern_counts(kp_plan *p, const int64_t *d_kmerM, const int64_t *d_kmerU
     if (n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     KP_CUDA(cudaSetDevice(p->device));
-    unsigned long long *d_pat = nullptr;
-    long long *d_out = nullptr;
-    KP_CUDA(cudaMallocAsync(&d_pat, n * 8, st));
-    KP_CUDA(cudaMallocAsync(&d_out, n * 16, st));
+    if (scratch_reserve(p, n * 24, st)) return 1;
+    unsigned long long *d_pat = (unsigned long long *)p->d_scratch;
+    long long *d_out = (long long *)(d_pat + n);
     KP_CUDA(cudaMemcpyAsync(d_pat, h_patnums, n * 8, cudaMemcpyHostToDevice, st));
     kp_pattern_counts_kernel<<<(int)n, 256, 0, st>>>(p->d_tab, p->host.nkmer, (const long long *)d_kmerM,
                                                      (const long long *)d_kmerU, d_pat, d_out, d_out + n);
@@ -474,8 +499,6 @@ int kp_pattern_counts(kp_plan *p, const int64_t *d_kmerM, const int64_t *d_kmerU
     KP_CUDA(cudaGetLastError());
     KP_CUDA(cudaMemcpyAsync(h_M, d_out, n * 8, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaMemcpyAsync(h_U, d_out + n, n * 8, cudaMemcpyDeviceToHost, st));
-    KP_CUDA(cudaFreeAsync(d_pat, st));
-    KP_CUDA(cudaFreeAsync(d_out, st));
     KP_CUDA(cudaStreamSynchronize(st));
     return 0;
 }

@@ -748,43 +748,83 @@ __device__ uint8_t kp_split_code_dev(const KpTables &tb, const uint16_t *srow_of
 // ---------------------------------------------------------------------------------------------------
 struct KpBtNode { unsigned long long pat, key; };
 
-__global__ void __launch_bounds__(256) kp_backtrack_kernel(const KpTables *tab, const uint8_t *rowtab, const float *best,
-                                                           const uint16_t *flags, unsigned long long top, KpBtNode *fa,
-                                                           KpBtNode *fb, KpBtNode *leaves, unsigned long long cap,
-                                                           unsigned long long *out_counts /* [0]=nleaves [1]=overflow */)
+// One launch per depth of the partition tree, one warp per node: lane e evaluates the splits of effective
+// position e (their 2 x nsplit child reads are independent and overlap), then the warp takes the
+// lexicographic minimum of (child sum, scan rank).  ctr: [0] leaves, [1] overflow flag, [2 + d] nodes at depth d.
+__global__ void __launch_bounds__(256) kp_backtrack_level_kernel(const KpTables *tab, const uint8_t *rowtab, const float *best,
+                                                                 const uint16_t *flags, int depth, const KpBtNode *cur,
+                                                                 KpBtNode *nxt, KpBtNode *leaves, unsigned long long cap,
+                                                                 unsigned long long *ctr)
 {
     const KpTables &tb = *tab;
     const uint16_t *srow_of_row = (const uint16_t *)(rowtab + tb.rt_srow_of_row);
-    __shared__ unsigned long long s_ncur, s_nnext, s_nleaf;
-    __shared__ int s_over;
-    if (threadIdx.x == 0) { s_ncur = 1; s_nnext = 0; s_nleaf = 0; s_over = 0; fa[0].pat = top; fa[0].key = 0; }
-    __syncthreads();
-    KpBtNode *cur = fa, *nxt = fb;
-    for (int depth = 0; depth < 64; depth++) {
-        unsigned long long ncur = s_ncur;
-        if (ncur == 0) break;
-        for (unsigned long long i = threadIdx.x; i < ncur; i += blockDim.x) {
-            KpBtNode nd = cur[i];
-            unsigned long long p1 = 0, p2 = 0;
-            uint8_t code = kp_split_code_dev(tb, srow_of_row, best, flags, nd.pat, &p1, &p2);
-            if (code == 0xFF) {
-                unsigned long long li = atomicAdd(&s_nleaf, 1ULL);
-                if (li < cap) leaves[li] = nd; else s_over = 1;
-                continue;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long ncur = ctr[2 + depth];
+    const unsigned long long nw = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < ncur; i += nw) {
+        KpBtNode nd = cur[i];
+        KpLoc L = kp_locate_dev(tb, srow_of_row, nd.pat);
+        bool kept = (flags[L.tile * tb.rp + L.srow] >> L.d0) & 1u;
+        float bv = __int_as_float(0x7f800000);
+        int code = 0x7fffffff;
+        unsigned long long b1 = 0, b2 = 0;
+        if (!kept && lane < tb.npos) {
+            const int e = lane;
+            unsigned long long w = tb.extw[e];
+            int d = (int)((nd.pat / w) % tb.radix[e]);
+            uint32_t m = tb.digit_mask[e][d];
+            const int ns = tb.ms_n[m];
+            float v[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                v[j] = __int_as_float(0x7f800000);
+                if (j < ns) {
+                    int c1 = tb.mask_digit[e][tb.ms_c1[m][j]], c2 = tb.mask_digit[e][tb.ms_c2[m][j]];
+                    v[j] = __fadd_rn(kp_best_at(tb, srow_of_row, best, nd.pat - (unsigned long long)(d - c1) * w),
+                                     kp_best_at(tb, srow_of_row, best, nd.pat - (unsigned long long)(d - c2) * w));
+                }
             }
-            unsigned long long ni = atomicAdd(&s_nnext, 2ULL);
-            if (ni + 2 > cap) { s_over = 1; continue; }
-            nxt[ni].pat = p1;
-            nxt[ni].key = nd.key;
-            nxt[ni + 1].pat = p2;
-            nxt[ni + 1].key = nd.key | (1ULL << (63 - depth));
+#pragma unroll
+            for (int j = 0; j < 7; j++)
+                if (j < ns && v[j] < bv) {
+                    bv = v[j];
+                    code = tb.pos_id[e] * 8 + j;
+                    b1 = nd.pat - (unsigned long long)(d - (int)tb.mask_digit[e][tb.ms_c1[m][j]]) * w;
+                    b2 = nd.pat - (unsigned long long)(d - (int)tb.mask_digit[e][tb.ms_c2[m][j]]) * w;
+                }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) { s_ncur = s_over ? 0 : s_nnext; s_nnext = 0; }
-        __syncthreads();
-        KpBtNode *t = cur; cur = nxt; nxt = t;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {   // first split in scan order among the minima
+            float ov = __shfl_down_sync(0xffffffffu, bv, o);
+            int oc = __shfl_down_sync(0xffffffffu, code, o);
+            unsigned long long o1 = __shfl_down_sync(0xffffffffu, b1, o), o2 = __shfl_down_sync(0xffffffffu, b2, o);
+            if (ov < bv || (ov == bv && oc < code)) { bv = ov; code = oc; b1 = o1; b2 = o2; }
+        }
+        if (lane == 0) {
+            if (kept || code == 0x7fffffff) {
+                unsigned long long li = atomicAdd(&ctr[0], 1ULL);
+                if (li < cap) leaves[li] = nd; else ctr[1] = 1;
+            } else if (depth >= 63) {
+                ctr[1] = 1;
+            } else {
+                unsigned long long ni = atomicAdd(&ctr[2 + depth + 1], 2ULL);
+                if (ni + 2 > cap) ctr[1] = 1;
+                else {
+                    nxt[ni].pat = b1;
+                    nxt[ni].key = nd.key;
+                    nxt[ni + 1].pat = b2;
+                    nxt[ni + 1].key = nd.key | (1ULL << (63 - depth));
+                }
+            }
+        }
     }
-    if (threadIdx.x == 0) { out_counts[0] = s_nleaf; out_counts[1] = (unsigned long long)(s_over || s_ncur != 0); }
+}
+
+__global__ void kp_backtrack_init_kernel(KpBtNode *fa, unsigned long long top, unsigned long long *ctr)
+{
+    if (threadIdx.x < 80) ctr[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) { fa[0].pat = top; fa[0].key = 0; ctr[2] = 1; }
 }
 
 // rank sort by key (keys are distinct): out[rank] = pat
@@ -794,17 +834,19 @@ __global__ void kp_backtrack_sort_kernel(const KpBtNode *leaves, const unsigned 
     unsigned long long n = counts[0];
     if (n > cap) n = cap;
     __shared__ unsigned long long keys[256];
-    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    unsigned long long mykey = i < n ? leaves[i].key : 0, rank = 0;
-    for (unsigned long long base = 0; base < n; base += 256) {
-        unsigned long long j = base + threadIdx.x;
-        keys[threadIdx.x] = j < n ? leaves[j].key : ~0ULL;
-        __syncthreads();
-        unsigned long long lim = n - base < 256 ? n - base : 256;
-        for (unsigned long long t = 0; t < lim; t++) rank += keys[t] < mykey;
-        __syncthreads();
+    for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x; i0 < n; i0 += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long i = i0 + threadIdx.x;
+        unsigned long long mykey = i < n ? leaves[i].key : 0, rank = 0;
+        for (unsigned long long base = 0; base < n; base += 256) {
+            unsigned long long j = base + threadIdx.x;
+            keys[threadIdx.x] = j < n ? leaves[j].key : ~0ULL;
+            __syncthreads();
+            unsigned long long lim = n - base < 256 ? n - base : 256;
+            for (unsigned long long t = 0; t < lim; t++) rank += keys[t] < mykey;
+            __syncthreads();
+        }
+        if (i < n) out[rank] = leaves[i].pat;
     }
-    if (i < n) out[rank] = leaves[i].pat;
 }
 
 // split codes of arbitrary patterns (test hook and output stage)

@@ -38,6 +38,9 @@ class PartitionPlan:
         self.info = info
         self.npat, self.nkmer = int(info.npat), int(info.nkmer)
         self._buf = {}
+        off = ctypes.c_uint64()
+        check(self.lib.kp_pattern_offset(h, self.npat - 1, ctypes.byref(off), None, None), "kp_pattern_offset")
+        self.top_elem = int(off.value)
 
     def __del__(self):
         try:
@@ -118,8 +121,8 @@ class PartitionPlan:
         return best, kept
 
     def top_score(self, table):
-        """np.float32 value of the general pattern in a device table."""
-        return self.gather(table, self.npat - 1, 1)[0]
+        """np.float32 value of the general pattern in a device table (one 4-byte device -> host read)."""
+        return np.float32(table[self.top_elem].item())
 
     # -- K5: backtrack ---------------------------------------------------------------------------
     def backtrack(self, best, kept, cap=65536):
