@@ -90,13 +90,9 @@ int kp_expand_counts(kp_plan *plan, const int64_t *d_kmerM, const int64_t *d_kme
  * is not stored: it is the first split in the reference's scan order whose float32 child sum equals the
  * minimum, and kp_backtrack / kp_split_codes re-derive it from d_best.
  * max_count: upper bound of any pattern count (n_mut + n_unmut); selects 32- or 64-bit on-chip counts.
- * Workspace: d_self float32[table_elems] and d_rup uint16[kept_elems] receive the self-score of every
- * pattern (K3: float64 score rounded to float32, plus a "rounded up" bit that keeps the reference's
- * float64 compare exact); K4 (the min-plus recurrence) reads them.
  */
 int kp_dp_single(kp_plan *plan, const int64_t *d_expM, const int64_t *d_expU, uint64_t max_count, double alpha,
-                 double beta, double penalty, float *d_self, uint16_t *d_rup, float *d_best, uint16_t *d_kept,
-                 void *stream);
+                 double beta, double penalty, float *d_best, uint16_t *d_kept, void *stream);
 
 /*
  * K5.  Partition of the general pattern, dense pattern numbers in the reference's emission order.
@@ -123,14 +119,12 @@ int kp_gather_kept(kp_plan *plan, const uint16_t *d_kept, uint64_t first, uint64
  * fold's held-out counts (both from kp_expand_counts); train counts are formed on device as
  * total - held-out.  d_train, d_test: float32[table_elems] each: training loss of the best partition of
  * every pattern and the held-out loss of that same partition.
- * Workspace: d_self, d_tself float32[table_elems], d_rup uint16[kept_elems] (self-scores, see kp_dp_single).
  * h_top[2]: train and held-out loss of the general pattern (written after synchronising `stream`);
  * may be NULL to leave the result on the device and not synchronise.
  */
 int kp_dp_cv_job(kp_plan *plan, const int64_t *d_expMtot, const int64_t *d_expUtot, const int64_t *d_expMtest,
                  const int64_t *d_expUtest, uint64_t max_count, double alpha, double beta_fold, double penalty,
-                 float *d_self, float *d_tself, uint16_t *d_rup, float *d_train, float *d_test, float *h_top,
-                 void *stream);
+                 float *d_train, float *d_test, float *h_top, void *stream);
 
 /* Counts of arbitrary patterns (dense numbers) straight from the k-mer tables.  Synchronises. */
 int kp_pattern_counts(kp_plan *plan, const int64_t *d_kmerM, const int64_t *d_kmerU, const uint64_t *h_patnums,

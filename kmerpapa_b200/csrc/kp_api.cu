@@ -43,48 +43,31 @@ struct kp_plan {
     unsigned char *d_scratch = nullptr;  // staging for the small host<->device exchanges (grown on demand)
     size_t scratch_cap = 0;
     uint64_t launches = 0;
-    int nwarps = 0;          // warps (= tiles in flight) per CTA of the DP kernel
+    int nwarps[2][2] = {{0, 0}, {0, 0}};  // warps (= tiles in flight) per CTA of the DP kernel [cv][wide]
     size_t smem_optin = 0;
 };
 
-template <bool CV>
+template <bool CV, bool WIDE>
 static const void *dp_kernel_for_radix(int r0)
 {
     switch (r0) {
-    case 1: return (const void *)kp_dp_rows_kernel<1, CV>;
-    case 3: return (const void *)kp_dp_rows_kernel<3, CV>;
-    case 7: return (const void *)kp_dp_rows_kernel<7, CV>;
-    default: return (const void *)kp_dp_rows_kernel<15, CV>;
+    case 1: return (const void *)kp_dp_rows_kernel<1, CV, WIDE>;
+    case 3: return (const void *)kp_dp_rows_kernel<3, CV, WIDE>;
+    case 7: return (const void *)kp_dp_rows_kernel<7, CV, WIDE>;
+    default: return (const void *)kp_dp_rows_kernel<15, CV, WIDE>;
     }
 }
 
 template <int R0>
-static void launch_dp_r0(bool cv, int grid, int threads, size_t smem, cudaStream_t st, const KpDpParams &prm)
-{
-    if (!cv) kp_dp_rows_kernel<R0, false><<<grid, threads, smem, st>>>(prm);
-    else kp_dp_rows_kernel<R0, true><<<grid, threads, smem, st>>>(prm);
-}
-
-template <int R0>
-static void launch_score_r0(bool cv, bool wide, int grid, size_t smem, cudaStream_t st, const KpScoreParams &prm)
+static void launch_dp_r0(bool cv, bool wide, int grid, int threads, size_t smem, cudaStream_t st, const KpDpParams &prm)
 {
     if (!cv) {
-        if (wide) kp_score_kernel<R0, false, true><<<grid, KP_SCORE_NT, smem, st>>>(prm);
-        else kp_score_kernel<R0, false, false><<<grid, KP_SCORE_NT, smem, st>>>(prm);
+        if (wide) kp_dp_rows_kernel<R0, false, true><<<grid, threads, smem, st>>>(prm);
+        else kp_dp_rows_kernel<R0, false, false><<<grid, threads, smem, st>>>(prm);
     } else {
-        if (wide) kp_score_kernel<R0, true, true><<<grid, KP_SCORE_NT, smem, st>>>(prm);
-        else kp_score_kernel<R0, true, false><<<grid, KP_SCORE_NT, smem, st>>>(prm);
+        if (wide) kp_dp_rows_kernel<R0, true, true><<<grid, threads, smem, st>>>(prm);
+        else kp_dp_rows_kernel<R0, true, false><<<grid, threads, smem, st>>>(prm);
     }
-}
-
-template <int R0>
-static cudaError_t score_attr_r0(int bytes)
-{
-    cudaError_t e;
-    if ((e = cudaFuncSetAttribute(kp_score_kernel<R0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
-    if ((e = cudaFuncSetAttribute(kp_score_kernel<R0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
-    if ((e = cudaFuncSetAttribute(kp_score_kernel<R0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
-    return cudaFuncSetAttribute(kp_score_kernel<R0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 extern "C" {
@@ -92,7 +75,11 @@ extern "C" {
 const char *kp_last_error(void) { return g_err.c_str(); }
 int kp_version(void) { return 100; }
 
-static const void *dp_kernel_ptr(int r0, bool cv) { return cv ? dp_kernel_for_radix<true>(r0) : dp_kernel_for_radix<false>(r0); }
+static const void *dp_kernel_ptr(int r0, bool cv, bool wide)
+{
+    if (!cv) return wide ? dp_kernel_for_radix<false, true>(r0) : dp_kernel_for_radix<false, false>(r0);
+    return wide ? dp_kernel_for_radix<true, true>(r0) : dp_kernel_for_radix<true, false>(r0);
+}
 
 int kp_plan_create(const char *gen_pat, int device, kp_plan **out)
 {
@@ -123,24 +110,17 @@ int kp_plan_create(const char *gen_pat, int device, kp_plan **out)
     KP_CUDA(cudaMemset(p->d_err, 0, sizeof(int)));
     KP_CUDA(cudaMalloc(&p->d_counters, sizeof(uint32_t) * 64));
     p->smem_optin = prop.sharedMemPerBlockOptin;
-    {
-        size_t fixed = t.rt_bytes, per_warp = t.warp_smem_bytes;
-        int nw = fixed < p->smem_optin ? (int)((p->smem_optin - fixed) / per_warp) : 0;
-        if (nw > KP_MAX_WARPS) nw = KP_MAX_WARPS;
-        p->nwarps = nw;
-        // the attribute is per function, not per plan: always raise it to the device maximum
-        for (int cv = 0; cv < 2; cv++)
-            KP_CUDA(cudaFuncSetAttribute(dp_kernel_ptr(t.r0, cv), cudaFuncAttributeMaxDynamicSharedMemorySize,
+    for (int cv = 0; cv < 2; cv++)
+        for (int wide = 0; wide < 2; wide++) {
+            size_t fixed = 2048 + t.rt_bytes, per_warp = t.warp_smem_bytes[cv][wide];
+            int nw = fixed < p->smem_optin ? (int)((p->smem_optin - fixed) / per_warp) : 0;
+            int cap = cv ? KP_MAX_WARPS_CV : KP_MAX_WARPS;
+            if (nw > cap) nw = cap;
+            p->nwarps[cv][wide] = nw;
+            // the attribute is per function, not per plan: always raise it to the device maximum
+            KP_CUDA(cudaFuncSetAttribute(dp_kernel_ptr(t.r0, cv, wide), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)prop.sharedMemPerBlockOptin));
-        cudaError_t e2;
-        switch (t.r0) {
-        case 1: e2 = score_attr_r0<1>((int)prop.sharedMemPerBlockOptin); break;
-        case 3: e2 = score_attr_r0<3>((int)prop.sharedMemPerBlockOptin); break;
-        case 7: e2 = score_attr_r0<7>((int)prop.sharedMemPerBlockOptin); break;
-        default: e2 = score_attr_r0<15>((int)prop.sharedMemPerBlockOptin); break;
         }
-        KP_CUDA(e2);
-    }
     *out = p;
     return 0;
 }
@@ -183,7 +163,7 @@ int kp_plan_get_info(const kp_plan *p, kp_plan_info *o)
     o->register_radix = (uint32_t)t.r0;
     o->rows = (uint32_t)t.nrows;
     o->rounds = (uint32_t)t.nrounds;
-    o->warps_per_cta = (uint32_t)p->nwarps;
+    o->warps_per_cta = (uint32_t)p->nwarps[0][0];
     o->high_levels = (uint32_t)(p->host.hl_off.size() - 1);
     o->sm_count = (uint32_t)p->sm_count;
     return 0;
@@ -274,30 +254,9 @@ int kp_expand_counts(kp_plan *p, const int64_t *d_kmerM, const int64_t *d_kmerU,
     return 0;
 }
 
-static int launch_score(kp_plan *p, bool cv, bool wide, const KpScoreParams &prm, cudaStream_t st)
+static int launch_dp(kp_plan *p, bool cv, bool wide, KpDpParams prm, cudaStream_t st)
 {
-    const KpTables &t = p->host.t;
-    size_t sm = 2048 + t.rt_bytes + (size_t)KP_SCORE_TPC * t.tile_kmers * (cv ? 4 : 2) * (wide ? 8 : 4) + KP_SCORE_TPC * 4 + 16;
-    if (sm > p->smem_optin) return fail("scoring kernel does not fit in shared memory for this tile shape");
-    uint64_t nchunks = ((uint64_t)t.ntiles + KP_SCORE_TPC - 1) / KP_SCORE_TPC;
-    uint64_t grid = nchunks;
-    uint64_t cap = (uint64_t)p->sm_count * 8;
-    if (grid > cap) grid = cap;
-    switch (t.r0) {
-    case 1: launch_score_r0<1>(cv, wide, (int)grid, sm, st, prm); break;
-    case 3: launch_score_r0<3>(cv, wide, (int)grid, sm, st, prm); break;
-    case 7: launch_score_r0<7>(cv, wide, (int)grid, sm, st, prm); break;
-    default: launch_score_r0<15>(cv, wide, (int)grid, sm, st, prm); break;
-    }
-    p->launches++;
-    KP_CUDA(cudaGetLastError());
-    return 0;
-}
-
-static int launch_dp(kp_plan *p, bool cv, KpDpParams prm, cudaStream_t st)
-{
-    int nw = p->nwarps;
-    if (cv && nw > KP_MAX_WARPS_CV) nw = KP_MAX_WARPS_CV;
+    int nw = p->nwarps[cv][wide];
     if (nw < 1) return fail("DP kernel does not fit in shared memory for this tile shape");
     size_t nhl = p->host.hl_off.size() - 1;
     const KpTables &t = p->host.t;
@@ -309,6 +268,7 @@ static int launch_dp(kp_plan *p, bool cv, KpDpParams prm, cudaStream_t st)
         prm.tile_list = p->d_tiles + lo;
         prm.ntiles_wave = (uint32_t)(hi - lo);
         prm.counter = p->d_counters + l;
+        prm.leaf_wave = (l == 0);
         uint64_t ntile = hi - lo;
         int warps = nw;
         if (ntile < (uint64_t)p->sm_count * nw) {  // small wave: spread the tiles over all SMs
@@ -317,12 +277,12 @@ static int launch_dp(kp_plan *p, bool cv, KpDpParams prm, cudaStream_t st)
         }
         uint64_t grid = (ntile + warps - 1) / warps;
         if (grid > (uint64_t)p->sm_count) grid = p->sm_count;
-        size_t sm = t.rt_bytes + (size_t)warps * t.warp_smem_bytes;
+        size_t sm = 2048 + t.rt_bytes + (size_t)warps * t.warp_smem_bytes[cv][wide];
         switch (t.r0) {
-        case 1: launch_dp_r0<1>(cv, (int)grid, warps * 32, sm, st, prm); break;
-        case 3: launch_dp_r0<3>(cv, (int)grid, warps * 32, sm, st, prm); break;
-        case 7: launch_dp_r0<7>(cv, (int)grid, warps * 32, sm, st, prm); break;
-        default: launch_dp_r0<15>(cv, (int)grid, warps * 32, sm, st, prm); break;
+        case 1: launch_dp_r0<1>(cv, wide, (int)grid, warps * 32, sm, st, prm); break;
+        case 3: launch_dp_r0<3>(cv, wide, (int)grid, warps * 32, sm, st, prm); break;
+        case 7: launch_dp_r0<7>(cv, wide, (int)grid, warps * 32, sm, st, prm); break;
+        default: launch_dp_r0<15>(cv, wide, (int)grid, warps * 32, sm, st, prm); break;
         }
         p->launches++;
     }
@@ -331,62 +291,42 @@ static int launch_dp(kp_plan *p, bool cv, KpDpParams prm, cudaStream_t st)
 }
 
 int kp_dp_single(kp_plan *p, const int64_t *d_expM, const int64_t *d_expU, uint64_t max_count, double alpha, double beta,
-                 double penalty, float *d_self, uint16_t *d_rup, float *d_best, uint16_t *d_kept, void *stream)
+                 double penalty, float *d_best, uint16_t *d_kept, void *stream)
 {
     if (!p) return fail("kp_dp_single: null plan");
     KP_CUDA(cudaSetDevice(p->device));
     bool wide = max_count > 0xFFFFFFFFull;
-    KpScoreParams sp;
-    memset(&sp, 0, sizeof sp);
-    sp.tab = p->d_tab;
-    sp.rowtab = p->d_rowtab;
-    sp.e0 = (const long long *)d_expM;
-    sp.e1 = (const long long *)d_expU;
-    sp.alpha = alpha; sp.beta = beta; sp.penalty = penalty;
-    sp.self = d_self;
-    sp.rup = d_rup;
-    if (launch_score(p, false, wide, sp, (cudaStream_t)stream)) return 1;
     KpDpParams prm;
     memset(&prm, 0, sizeof prm);
     prm.tab = p->d_tab;
     prm.rowtab = p->d_rowtab;
-    prm.self = d_self;
-    prm.rup = d_rup;
+    prm.e0 = (const long long *)d_expM;
+    prm.e1 = (const long long *)d_expU;
+    prm.alpha = alpha; prm.beta = beta; prm.penalty = penalty;
     prm.best = d_best;
     prm.flags = d_kept;
-    return launch_dp(p, false, prm, (cudaStream_t)stream);
+    return launch_dp(p, false, wide, prm, (cudaStream_t)stream);
 }
 
 int kp_dp_cv_job(kp_plan *p, const int64_t *d_expMtot, const int64_t *d_expUtot, const int64_t *d_expMtest,
                  const int64_t *d_expUtest, uint64_t max_count, double alpha, double beta_fold, double penalty,
-                 float *d_self, float *d_tself, uint16_t *d_rup, float *d_train, float *d_test, float *h_top, void *stream)
+                 float *d_train, float *d_test, float *h_top, void *stream)
 {
     if (!p) return fail("kp_dp_cv_job: null plan");
     KP_CUDA(cudaSetDevice(p->device));
     bool wide = max_count > 0xFFFFFFFFull;
-    KpScoreParams sp;
-    memset(&sp, 0, sizeof sp);
-    sp.tab = p->d_tab;
-    sp.rowtab = p->d_rowtab;
-    sp.e0 = (const long long *)d_expMtot;
-    sp.e1 = (const long long *)d_expUtot;
-    sp.e2 = (const long long *)d_expMtest;
-    sp.e3 = (const long long *)d_expUtest;
-    sp.alpha = alpha; sp.beta = beta_fold; sp.penalty = penalty;
-    sp.self = d_self;
-    sp.tself = d_tself;
-    sp.rup = d_rup;
-    if (launch_score(p, true, wide, sp, (cudaStream_t)stream)) return 1;
     KpDpParams prm;
     memset(&prm, 0, sizeof prm);
     prm.tab = p->d_tab;
     prm.rowtab = p->d_rowtab;
-    prm.self = d_self;
-    prm.tself = d_tself;
-    prm.rup = d_rup;
+    prm.e0 = (const long long *)d_expMtot;
+    prm.e1 = (const long long *)d_expUtot;
+    prm.e2 = (const long long *)d_expMtest;
+    prm.e3 = (const long long *)d_expUtest;
+    prm.alpha = alpha; prm.beta = beta_fold; prm.penalty = penalty;
     prm.best = d_train;
     prm.test = d_test;
-    if (launch_dp(p, true, prm, (cudaStream_t)stream)) return 1;
+    if (launch_dp(p, true, wide, prm, (cudaStream_t)stream)) return 1;
     if (h_top) {
         uint64_t tile; uint32_t srow, d0;
         kp_locate(p->host, p->host.npat - 1, &tile, &srow, &d0);

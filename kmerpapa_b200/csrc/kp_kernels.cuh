@@ -2,28 +2,30 @@
 //
 // Work decomposition (geometry in kp_tables.h, rationale in DESIGN.md):
 //
-//  K3  kp_score_kernel      float64 self-score of every pattern (glibc-exact log), embarrassingly
-//                           parallel, high occupancy.  A thread owns one row of one tile: counts of the row
-//                           from the tile's base k-mers (shared memory) by subset sums, then r0 scores.
-//                           It stores RN_f32(s) plus one "rounded up" bit per pattern; the reference's
-//                           float64 compare  s < (double)best  is exactly
-//                           sf < best || (sf == best && rounded_up)  with sf = RN_f32(s), and the value it
-//                           stores on a win is sf.  (CV: also the held-out loss of the unsplit pattern.)
-//
-//  K4  kp_dp_rows_kernel    the min-plus recurrence.  One WARP owns one tile at a time, one LANE owns one
-//                           row of it, the r0 (<= 15) sub-patterns of the register position live in
-//                           registers.  No block-wide barrier in steady state.  Rows are visited in a
-//                           precomputed schedule (rounds of <= 32 rows whose children are complete).
-//                           Per row: running minimum over the HIGH-position splits, streamed from two child
-//                           tiles each with coalesced 16-byte loads (software-pipelined two splits deep);
-//                           running minimum over the CROSS-row splits from the tile's finished rows in
-//                           shared memory; in-register splits of the register position interleaved with the
-//                           self-score compare; one coalesced 16-byte store per group, one 16-bit
-//                           "kept whole" mask per row.
-//                           The single DP only keeps the minimum (fminf); which split won is re-derived by
-//                           the backtrack from the stored scores (first split in scan order that reproduces
-//                           the minimum).  The CV job needs the held-out loss of the winning split, so it
-//                           tracks (value, scan rank) lexicographically.
+//  K3+K4  kp_dp_rows_kernel   the min-plus recurrence with the float64 self-score fused in, lazily.
+//      One WARP owns one tile at a time, one LANE owns one row of it, and the r0 (<= 15) sub-patterns of
+//      the register position of that row live in registers.  No block-wide barrier in steady state.
+//      Per tile:
+//        phase D  (single DP) stream the two child tiles of every HIGH-position split for all rows, 32
+//                 consecutive rows at a time, coalesced 16-byte loads, one flattened two-deep software
+//                 pipeline; the running minimum of each row is parked in shared memory.  (The CV job
+//                 streams inside the rounds because it also has to track which split won.)
+//        rounds   rows are visited in a precomputed schedule (<= 32 rows whose children are complete):
+//                 running minimum over the CROSS-row splits from the tile's finished rows in shared memory;
+//                 counts of the row from the tile's base k-mers by subset sums;
+//                 SCORE FILTER: a float32 estimate of every self-score with a rigorous error margin; a
+//                 pattern whose estimate minus margin already exceeds its best split so far can never be
+//                 kept whole (later in-register splits only lower the best split), so its exact score is
+//                 never needed;
+//                 EXACT SCORE for the remaining patterns only: float64, glibc-exact log (kp_math.cuh), in a
+//                 rolled loop (the code exists once); RN_f32(s) and a "rounded up" bit are kept, because
+//                 the reference's float64 compare  s < (double)best  is exactly
+//                 sf < best || (sf == best && rounded_up), and the value it stores on a win is sf;
+//                 in-register splits of the register position interleaved with that compare, fully
+//                 unrolled; one coalesced 16-byte store per group, one 16-bit "kept whole" mask per row.
+//      The single DP only keeps the minimum (fminf); which split won is re-derived by the backtrack from
+//      the stored scores (first split in scan order that reproduces the minimum).  The CV job needs the
+//      held-out loss of the winning split, so it tracks (value, scan rank) lexicographically.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -33,8 +35,6 @@
 
 #define KP_MAX_WARPS 14      // single DP: tiles in flight per SM (<= 128 registers per thread)
 #define KP_MAX_WARPS_CV 12   // CV job: fewer warps, up to 168 registers per thread (winner codes + held-out values)
-#define KP_SCORE_NT 256     // threads per CTA of the scoring kernel
-#define KP_SCORE_TPC 8      // tiles per chunk of the scoring kernel
 
 template <bool WIDE> struct KpCnt { typedef unsigned int type; };
 template <> struct KpCnt<true> { typedef unsigned long long type; };
@@ -111,142 +111,29 @@ __device__ __noinline__ void kp_leaf_cv_nl(unsigned long long Mtr, unsigned long
     *test = b;
 }
 
-// ---------------------------------------------------------------------------------------------------
-// K3: self-scores
-// ---------------------------------------------------------------------------------------------------
-struct KpScoreParams {
-    const KpTables *tab;
-    const uint8_t *rowtab;
-    const long long *e0, *e1, *e2, *e3;  // single: M, U.  CV: Mtot, Utot, Mtest, Utest  [ntiles][tile_kmers]
-    double alpha, beta, penalty;
-    float *self;        // RN_f32 of the self-score (train loss of the unsplit pattern)
-    float *tself;       // CV: held-out loss of the unsplit pattern
-    uint16_t *rup;      // per row: bit d set = RN_f32(s) > s
-};
-
-template <int R0, bool CV, bool WIDE>
-__global__ void __launch_bounds__(KP_SCORE_NT) kp_score_kernel(const KpScoreParams p)
+// digit -> covered base digits of the register position (digit space), run-time index (exact-score loop)
+__constant__ uint8_t kpc_bm1[4] = {1, 0, 0, 0};
+__constant__ uint8_t kpc_bm3[4] = {1, 2, 3, 0};
+__constant__ uint8_t kpc_bm7[8] = {1, 2, 4, 3, 5, 6, 7, 0};
+__constant__ uint8_t kpc_bm15[16] = {1, 2, 4, 8, 5, 10, 6, 9, 12, 3, 14, 13, 11, 7, 15, 0};
+template <int R0> __device__ __forceinline__ unsigned kp_bm(int d)
 {
-    typedef typename KpCnt<WIDE>::type C;
-    constexpr int NB = R0 == 15 ? 4 : (R0 == 7 ? 3 : (R0 == 3 ? 2 : 1));
-    constexpr int NG = (R0 + 3) / 4;
-    constexpr int CW = CV ? 4 : 2;
-    extern __shared__ __align__(16) unsigned char smem[];
-    const KpTables &tb = *p.tab;
-    const int nrows = tb.nrows, rp = tb.rp, nhigh = tb.nhigh;
-    const uint32_t tk = tb.tile_kmers, stride = tb.tile_stride, ntiles = tb.ntiles;
-    double2 *logtab = (double2 *)smem;
-    unsigned char *rt = smem + 2048;
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) logtab[i] = make_double2(kpc_logTab[2 * i], kpc_logTab[2 * i + 1]);
-    for (uint32_t i = threadIdx.x; i < tb.rt_bytes / 4; i += blockDim.x) ((uint32_t *)rt)[i] = ((const uint32_t *)p.rowtab)[i];
-    const uint8_t *row_level = rt + tb.rt_row_level;
-    const uint16_t *bs_off = (const uint16_t *)(rt + tb.rt_bs_off);
-    const uint16_t *bs = (const uint16_t *)(rt + tb.rt_bs);
-    C *bc = (C *)(rt + tb.rt_bytes);                                  // [TPC][tile_kmers][CW]
-    int *leaf_tile = (int *)((unsigned char *)bc + (size_t)KP_SCORE_TPC * tk * CW * sizeof(C));
-    const double alpha = p.alpha, beta = p.beta, penalty = p.penalty;
-    const KpLogK K = kp_logk_load();
+    return R0 == 15 ? kpc_bm15[d] : (R0 == 7 ? kpc_bm7[d] : (R0 == 3 ? kpc_bm3[d] : kpc_bm1[d]));
+}
 
-    const uint32_t nchunks = (ntiles + KP_SCORE_TPC - 1) / KP_SCORE_TPC;
-    for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-        const uint32_t tile0 = chunk * KP_SCORE_TPC;
-        const uint32_t nt = min((uint32_t)KP_SCORE_TPC, ntiles - tile0);
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < nt * tk; i += blockDim.x) {
-            size_t g = (size_t)tile0 * tk + i;
-            if (!CV) {
-                bc[i * CW + 0] = (C)p.e0[g];
-                bc[i * CW + 1] = (C)p.e1[g];
-            } else {
-                long long mt = p.e2[g], ut = p.e3[g];
-                bc[i * CW + 0] = (C)(p.e0[g] - mt);  // train = total - held-out
-                bc[i * CW + 1] = (C)(p.e1[g] - ut);
-                bc[i * CW + 2] = (C)mt;
-                bc[i * CW + 3] = (C)ut;
-            }
-        }
-        if (threadIdx.x < nt) {  // a tile holds k-mers iff every high digit is a single nucleotide
-            uint32_t x = tile0 + threadIdx.x;
-            int leaf = 1;
-            for (int h = 0; h < nhigh; h++) {
-                int e = tb.highpos[h];
-                if (x % tb.radix[e] >= tb.nbase[e]) leaf = 0;
-                x /= tb.radix[e];
-            }
-            leaf_tile[threadIdx.x] = leaf;
-        }
-        __syncthreads();
-        for (uint32_t idx = threadIdx.x; idx < nt * (uint32_t)nrows; idx += blockDim.x) {
-            const uint32_t tl = idx / (uint32_t)nrows, srow = idx - tl * (uint32_t)nrows;
-            const uint32_t tile = tile0 + tl;
-            C m[NB], u[NB], mt[CV ? NB : 1], ut[CV ? NB : 1];
-#pragma unroll
-            for (int b = 0; b < NB; b++) { m[b] = 0; u[b] = 0; if (CV) { mt[b] = 0; ut[b] = 0; } }
-            const C *tbc = bc + (size_t)tl * tk * CW;
-            for (int i = bs_off[srow]; i < bs_off[srow + 1]; i++) {
-                const C *q = tbc + (size_t)bs[i] * NB * CW;
-#pragma unroll
-                for (int b = 0; b < NB; b++) {
-                    m[b] += q[b * CW + 0];
-                    u[b] += q[b * CW + 1];
-                    if (CV) { mt[b] += q[b * CW + 2]; ut[b] += q[b * CW + 3]; }
-                }
-            }
-            const bool leafrow = leaf_tile[tl] && row_level[srow] == 0;
-            float2 *os = (float2 *)(p.self + (size_t)tile * stride) + 2 * srow;
-            float2 *ot = CV ? (float2 *)(p.tself + (size_t)tile * stride) + 2 * srow : nullptr;
-            uint32_t rupm = 0;
-            // two patterns per iteration: enough ILP for the FP64 pipe, small enough for the instruction cache
-#pragma unroll 1
-            for (int h = 0; h < NG * 2; h++) {
-                C Mx[2], Ux[2], Mtx[2], Utx[2];
-                // counts of the two patterns: subset sums with compile-time masks, selected by a uniform switch
-#define KP_PAIR(H)                                                                                          \
-    case H:                                                                                                 \
-        Mx[0] = kp_sum_bases<kp_bm_c<R0>(2 * H), NB, C>(m); Ux[0] = kp_sum_bases<kp_bm_c<R0>(2 * H), NB, C>(u);          \
-        Mx[1] = kp_sum_bases<kp_bm_c<R0>(2 * H + 1), NB, C>(m); Ux[1] = kp_sum_bases<kp_bm_c<R0>(2 * H + 1), NB, C>(u);  \
-        if (CV) {                                                                                           \
-            Mtx[0] = kp_sum_bases<kp_bm_c<R0>(2 * H), NB, C>(mt); Utx[0] = kp_sum_bases<kp_bm_c<R0>(2 * H), NB, C>(ut);  \
-            Mtx[1] = kp_sum_bases<kp_bm_c<R0>(2 * H + 1), NB, C>(mt); Utx[1] = kp_sum_bases<kp_bm_c<R0>(2 * H + 1), NB, C>(ut); \
-        }                                                                                                   \
-        break;
-                Mtx[0] = Mtx[1] = Utx[0] = Utx[1] = 0;
-                switch (h) {
-                    KP_PAIR(0) KP_PAIR(1) KP_PAIR(2) KP_PAIR(3) KP_PAIR(4) KP_PAIR(5) KP_PAIR(6)
-                default:
-                    KP_PAIR(7)
-                }
-#undef KP_PAIR
-                float sf[2], tf[2];
-#pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    const int d = 2 * h + c;
-                    sf[c] = 0.f; tf[c] = 0.f;
-                    if (d < R0) {
-                        double s_, t_ = 0.0, lp_, l1_;
-                        if (leafrow && d < NB) {
-                            if (!CV) s_ = kp_leaf_score_nl(Mx[c], Ux[c], alpha, beta, penalty, logtab);
-                            else kp_leaf_cv_nl(Mx[c], Ux[c], Mtx[c], Utx[c], alpha, beta, penalty, logtab, &s_, &t_);
-                        } else {
-                            s_ = kp_self_score_t<C>(Mx[c], Ux[c], alpha, beta, penalty, logtab, K, lp_, l1_);
-                            if (CV) t_ = kp_test_ll_t<C>(Mtx[c], Utx[c], lp_, l1_);
-                        }
-                        sf[c] = __double2float_rn(s_);
-                        if ((double)sf[c] > s_) rupm |= 1u << d;
-                        if (CV) tf[c] = __double2float_rn(t_);
-                    }
-                }
-                // element (d>>2, srow, d&3): float2 index ((h>>1)*rp + srow)*2 + (h&1)
-                os[(size_t)(h >> 1) * rp * 2 + (h & 1)] = make_float2(sf[0], sf[1]);
-                if (CV) ot[(size_t)(h >> 1) * rp * 2 + (h & 1)] = make_float2(tf[0], tf[1]);
-            }
-            p.rup[(size_t)tile * rp + srow] = (uint16_t)rupm;
-        }
-    }
+// Float32 estimate of the self-score (w_numba.py:56-61) for the score filter.  Relative error < 1e-5
+// (fast log: < 2^-21 absolute; log(1-p) by its series below p = 2^-5; no cancellation: both terms are >= 0);
+// the filter uses a margin of 2e-4 |s| + 0.01.  A NaN estimate (p == 0, ...) never skips the exact score.
+__device__ __forceinline__ float kp_score_estimate(float Mf, float Uf, float alpha, float ab, float penalty)
+{
+    float p = __fdividef(Mf + alpha, (Mf + Uf) + ab);
+    float lp = __logf(p);
+    float l1 = p < 0.03125f ? -p * (1.0f + p * (0.5f + p * (0.33333334f + 0.25f * p))) : __logf(1.0f - p);
+    return penalty - 2.0f * (Mf * lp + Uf * l1);
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K4: min-plus recurrence
+// K3+K4: lazily fused self-score + min-plus recurrence
 // ---------------------------------------------------------------------------------------------------
 struct KpDpParams {
     const KpTables *tab;
@@ -254,9 +141,9 @@ struct KpDpParams {
     const uint32_t *tile_list;  // tiles of this wave, ascending
     uint32_t ntiles_wave;
     uint32_t *counter;          // next unclaimed entry of tile_list (zeroed before the launch)
-    const float *self;          // K3 outputs
-    const float *tself;
-    const uint16_t *rup;
+    int leaf_wave;              // wave 0: rows of level 0 hold k-mers at the single-nucleotide digits
+    const long long *e0, *e1, *e2, *e3;  // single: M, U.  CV: Mtot, Utot, Mtest, Utest  [ntiles][tile_kmers]
+    double alpha, beta, penalty;
     float *best;        // single: best loss;  CV: train loss
     float *test;        // CV: held-out loss of the chosen partition
     uint16_t *flags;    // single: per row, bit d set = pattern kept whole
@@ -272,11 +159,9 @@ template <int R0, bool CV>
 struct KpRow {
     static constexpr int NG = (R0 + 3) / 4;
     float v[NG * 4];             // best (train) loss so far / final
-    float sv[NG * 4];            // self-score (RN_f32)
     float tv[CV ? NG * 4 : 1];   // CV: held-out loss of the current winner
-    float ts[CV ? NG * 4 : 1];   // CV: held-out loss of the unsplit pattern
     int rk[CV ? NG * 4 : 1];     // CV: code of the current winner, KP_NONE = none yet
-    uint32_t rup, flag;
+    uint32_t need, rup, flag;    // per digit: exact self-score available / it rounded up / kept whole
 };
 
 template <int R0, bool CV>
@@ -297,34 +182,46 @@ struct KpRowOps {
     }
 };
 
-template <int R0, bool CV>
+template <int R0, bool CV, bool WIDE>
 __global__ void __launch_bounds__((CV ? KP_MAX_WARPS_CV : KP_MAX_WARPS) * 32, 1) kp_dp_rows_kernel(const KpDpParams p)
 {
     typedef KpRow<R0, CV> Row;
     typedef KpRowOps<R0, CV> Ops;
+    typedef typename KpCnt<WIDE>::type C;
     constexpr int NG = Row::NG;
+    constexpr int NB = R0 == 15 ? 4 : (R0 == 7 ? 3 : (R0 == 3 ? 2 : 1));
+    constexpr int CW = CV ? 4 : 2;  // counters per base k-mer
 
     extern __shared__ __align__(16) unsigned char smem[];
     const KpTables &tb = *p.tab;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int rp = tb.rp, nrounds = tb.nrounds, nhigh = tb.nhigh;
-    const uint32_t stride = tb.tile_stride;
+    const uint32_t stride = tb.tile_stride, tk = tb.tile_kmers;
     const uint32_t rt_bytes = tb.rt_bytes;
+    const int maxhs = tb.maxhs;
 
-    unsigned char *rt = smem;
+    double2 *logtab = (double2 *)smem;
+    unsigned char *rt = smem + 2048;
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) logtab[i] = make_double2(kpc_logTab[2 * i], kpc_logTab[2 * i + 1]);
     for (uint32_t i = threadIdx.x; i < rt_bytes / 4; i += blockDim.x) ((uint32_t *)rt)[i] = ((const uint32_t *)p.rowtab)[i];
     __syncthreads();
     const uint16_t *round_start = (const uint16_t *)(rt + tb.rt_round_start);
+    const uint8_t *row_level = rt + tb.rt_row_level;
     const uint16_t *xs_off = (const uint16_t *)(rt + tb.rt_xs_off);
     const uint32_t *xs = (const uint32_t *)(rt + tb.rt_xs);
     const uint8_t *xsr = rt + tb.rt_xs_rank;
+    const uint16_t *bs_off = (const uint16_t *)(rt + tb.rt_bs_off);
+    const uint16_t *bs = (const uint16_t *)(rt + tb.rt_bs);
 
-    unsigned char *wm = smem + rt_bytes + (size_t)warp * tb.warp_smem_bytes;
+    unsigned char *wm = smem + 2048 + rt_bytes + (size_t)warp * tb.warp_smem_bytes[CV][WIDE];
     float4 *S = (float4 *)wm;                                  // [NG][rp]
-    uint32_t *hs1 = (uint32_t *)(wm + (size_t)NG * rp * 16);
-    uint32_t *hs2 = hs1 + KP_MAXHS;
-    uint8_t *hsr = (uint8_t *)(hs2 + KP_MAXHS);
-    int *s_nhs = (int *)(hsr + KP_MAXHS);
+    C *bc = (C *)(wm + (size_t)NG * rp * 16);                  // [tile_kmers][CW] base counts of the tile
+    uint32_t *hs1 = (uint32_t *)((unsigned char *)bc + (size_t)tk * CW * sizeof(C));
+    uint32_t *hs2 = hs1 + maxhs;
+    uint8_t *hsr = (uint8_t *)(hs2 + maxhs);
+    int *s_nhs = (int *)(hsr + ((maxhs + 3) & ~3));
+    const double alpha = p.alpha, beta = p.beta, penalty = p.penalty;
+    const float alpha_f = (float)alpha, ab_f = (float)(alpha + beta), penalty_f = (float)penalty;
 
     const float INF = __int_as_float(0x7f800000);
     const int rankbase = tb.estar >= 0 ? tb.pos_id[tb.estar] * 8 : 0;
@@ -366,16 +263,24 @@ __global__ void __launch_bounds__((CV ? KP_MAX_WARPS_CV : KP_MAX_WARPS) * 32, 1)
             }
             if (lane == 0) *s_nhs = total;
         }
+        // ---- base counts of the tile ----
+        for (uint32_t kl = lane; kl < tk; kl += 32) {
+            size_t g = (size_t)tile * tk + kl;
+            if (!CV) {
+                bc[kl * CW + 0] = (C)p.e0[g];
+                bc[kl * CW + 1] = (C)p.e1[g];
+            } else {
+                long long mt = p.e2[g], ut = p.e3[g];
+                bc[kl * CW + 0] = (C)(p.e0[g] - mt);  // train = total - held-out
+                bc[kl * CW + 1] = (C)(p.e1[g] - ut);
+                bc[kl * CW + 2] = (C)mt;
+                bc[kl * CW + 3] = (C)ut;
+            }
+        }
         __syncwarp();
         const int nhs = *s_nhs;
         const float *tbase = p.best;
         float4 *otile = (float4 *)(p.best + (size_t)tile * stride);
-        const float4 *stile = (const float4 *)(p.self + (size_t)tile * stride);
-        // the tile's self-scores are consumed round by round later on: pull them into L2 now
-        for (uint32_t off = lane * 32u; off < stride; off += 32u * 32u) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.self + (size_t)tile * stride + off));
-            if (CV) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.tself + (size_t)tile * stride + off));
-        }
 
         // ---- phase D (single DP): stream the child tiles of the high-position splits for ALL rows of the tile,
         //      32 consecutive rows at a time, two splits in flight; the running minimum of row r is parked
@@ -479,17 +384,6 @@ __global__ void __launch_bounds__((CV ? KP_MAX_WARPS_CV : KP_MAX_WARPS) * 32, 1)
             if (srow < round_start[rnd + 1]) {
                 Row r;
                 r.flag = 0;
-                // self-scores of the row: issued first, consumed last
-#pragma unroll
-                for (int g = 0; g < NG; g++) {
-                    float4 x = __ldcs(stile + g * rp + srow);  // read once: evict first
-                    r.sv[4 * g] = x.x; r.sv[4 * g + 1] = x.y; r.sv[4 * g + 2] = x.z; r.sv[4 * g + 3] = x.w;
-                    if (CV) {
-                        float4 y = __ldcs((const float4 *)(p.tself + (size_t)tile * stride) + g * rp + srow);
-                        r.ts[4 * g] = y.x; r.ts[4 * g + 1] = y.y; r.ts[4 * g + 2] = y.z; r.ts[4 * g + 3] = y.w;
-                    }
-                }
-                r.rup = p.rup[(size_t)tile * rp + srow];
 #pragma unroll
                 for (int c = 0; c < NG * 4; c++) { r.v[c] = INF; if (CV) { r.tv[c] = 0.f; r.rk[c] = KP_NONE; } }
 
@@ -528,6 +422,69 @@ __global__ void __launch_bounds__((CV ? KP_MAX_WARPS_CV : KP_MAX_WARPS) * 32, 1)
                     }
                 }
 
+                // ---- counts of this row at the single-nucleotide digits of the register position ----
+                C m[NB], u[NB], mt[CV ? NB : 1], ut[CV ? NB : 1];
+#pragma unroll
+                for (int b = 0; b < NB; b++) { m[b] = 0; u[b] = 0; if (CV) { mt[b] = 0; ut[b] = 0; } }
+                for (int i = bs_off[srow]; i < bs_off[srow + 1]; i++) {
+                    const C *q = bc + (size_t)bs[i] * NB * CW;
+#pragma unroll
+                    for (int b = 0; b < NB; b++) {
+                        m[b] += q[b * CW + 0];
+                        u[b] += q[b * CW + 1];
+                        if (CV) { mt[b] += q[b * CW + 2]; ut[b] += q[b * CW + 3]; }
+                    }
+                }
+                // ---- score filter: which patterns can still be kept whole? (r.v only decreases from here) ----
+                const bool leafrow = p.leaf_wave && row_level[srow] == 0;
+                uint32_t need = 0;
+                {
+                    float mf[NB], uf[NB];
+#pragma unroll
+                    for (int b = 0; b < NB; b++) { mf[b] = (float)m[b]; uf[b] = (float)u[b]; }
+#pragma unroll
+                    for (int d = 0; d < R0; d++) {
+                        float Mf = 0.f, Uf = 0.f;
+#pragma unroll
+                        for (int b = 0; b < NB; b++)
+                            if ((kp_bm_c<R0>(d) >> b) & 1) { Mf += mf[b]; Uf += uf[b]; }
+                        float est = kp_score_estimate(Mf, Uf, alpha_f, ab_f, penalty_f);
+                        float margin = 2e-4f * fabsf(est) + 0.01f;
+                        if (!(est - margin > r.v[d])) need |= 1u << d;
+                    }
+                    if (leafrow) need |= (1u << NB) - 1u;
+                }
+                // ---- exact float64 self-score of the patterns that passed the filter ----
+                float sfx[NG * 4], tfx[CV ? NG * 4 : 1];   // indexed at run time below: lives in local memory, rarely touched
+                uint32_t rupm = 0;
+                if (need) {
+                    const KpLogK K = kp_logk_load();
+                    uint32_t todo = need;
+                    while (todo) {
+                        const int d = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const unsigned bm = kp_bm<R0>(d);
+                        C M_ = 0, U_ = 0, Mt_ = 0, Ut_ = 0;
+#pragma unroll
+                        for (int b = 0; b < NB; b++)
+                            if ((bm >> b) & 1u) { M_ += m[b]; U_ += u[b]; if (CV) { Mt_ += mt[b]; Ut_ += ut[b]; } }
+                        double s_, t_ = 0.0, lp_, l1_;
+                        if (leafrow && d < NB) {
+                            if (!CV) s_ = kp_leaf_score_nl(M_, U_, alpha, beta, penalty, logtab);
+                            else kp_leaf_cv_nl(M_, U_, Mt_, Ut_, alpha, beta, penalty, logtab, &s_, &t_);
+                        } else {
+                            s_ = kp_self_score_t<C>(M_, U_, alpha, beta, penalty, logtab, K, lp_, l1_);
+                            if (CV) t_ = kp_test_ll_t<C>(Mt_, Ut_, lp_, l1_);
+                        }
+                        const float sf = __double2float_rn(s_);
+                        if ((double)sf > s_) rupm |= 1u << d;
+                        sfx[d] = sf;
+                        if (CV) tfx[d] = __double2float_rn(t_);
+                    }
+                }
+                r.need = need;
+                r.rup = rupm;
+
                 // ---- register position: in-register splits + self-score compare, digit by digit ----
                 // CV: fetch the held-out loss of a winner that came from memory (streamed or cross-row split)
                 auto fetch_test = [&](int d, int code) -> float {
@@ -544,11 +501,16 @@ __global__ void __launch_bounds__((CV ? KP_MAX_WARPS_CV : KP_MAX_WARPS) * 32, 1)
                 // reference: if s < (double)best: best = f32(s)   <=>   sf < best || (sf == best && sf > s)
 #define KP_FIN(D)                                                                                                \
     {                                                                                                            \
-        const bool self_ = r.sv[D] < r.v[D] || (r.sv[D] == r.v[D] && ((r.rup >> (D)) & 1u));                     \
+        bool self_ = false;                                                                                      \
+        float sf_ = 0.f;                                                                                         \
+        if ((r.need >> (D)) & 1u) {                                                                              \
+            sf_ = sfx[D];                                                                                        \
+            self_ = sf_ < r.v[D] || (sf_ == r.v[D] && ((r.rup >> (D)) & 1u));                                    \
+        }                                                                                                        \
         if (!CV) {                                                                                               \
-            if (self_) { r.v[D] = r.sv[D]; r.flag |= 1u << (D); }                                                \
+            if (self_) { r.v[D] = sf_; r.flag |= 1u << (D); }                                                    \
         } else {                                                                                                 \
-            if (self_) { r.v[D] = r.sv[D]; r.tv[D] = r.ts[D]; }                                                  \
+            if (self_) { r.v[D] = sf_; r.tv[D] = tfx[D]; }                                                       \
             else if ((r.rk[D] & 0xFF) != KP_INROW) r.tv[D] = fetch_test(D, r.rk[D]);                             \
         }                                                                                                        \
     }

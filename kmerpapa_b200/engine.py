@@ -113,11 +113,8 @@ class PartitionPlan:
         torch = _torch()
         best = self._buffer("best", int(self.info.table_elems), torch.float32)
         kept = self._buffer("kept", int(self.info.kept_elems), torch.int16)
-        selfs = self._buffer("self", int(self.info.table_elems), torch.float32)
-        rup = self._buffer("rup", int(self.info.kept_elems), torch.int16)
         check(self.lib.kp_dp_single(self.handle, eM.data_ptr(), eU.data_ptr(), int(max_count), float(alpha), float(beta),
-                                    float(penalty), selfs.data_ptr(), rup.data_ptr(), best.data_ptr(), kept.data_ptr(),
-                                    self._stream()), "kp_dp_single")
+                                    float(penalty), best.data_ptr(), kept.data_ptr(), self._stream()), "kp_dp_single")
         return best, kept
 
     def top_score(self, table):
@@ -158,15 +155,11 @@ class PartitionPlan:
         n = int(self.info.table_elems)
         train = self._buffer("cvtrain", n, torch.float32)
         test = self._buffer("cvtest", n, torch.float32)
-        selfs = self._buffer("self", n, torch.float32)
-        tselfs = self._buffer("tself", n, torch.float32)
-        rup = self._buffer("rup", int(self.info.kept_elems), torch.int16)
         top = (ctypes.c_float * 2)()
         check(self.lib.kp_dp_cv_job(self.handle, eMtot.data_ptr(), eUtot.data_ptr(), eMte.data_ptr(), eUte.data_ptr(),
-                                    int(max_count), float(alpha), float(beta), float(penalty), selfs.data_ptr(),
-                                    tselfs.data_ptr(), rup.data_ptr(), train.data_ptr(), test.data_ptr(),
-                                    ctypes.cast(top, ctypes.c_void_p) if read_top else None, self._stream()),
-              "kp_dp_cv_job")
+                                    int(max_count), float(alpha), float(beta), float(penalty), train.data_ptr(),
+                                    test.data_ptr(), ctypes.cast(top, ctypes.c_void_p) if read_top else None,
+                                    self._stream()), "kp_dp_cv_job")
         if not read_top:
             return train, test
         return np.float32(top[0]), np.float32(top[1])
