@@ -276,9 +276,9 @@ def bench_single(args, rank, world, local):
                    "loss": float(loss), "l2": "score+split tables 12.9 GB >> 126 MB L2, no flush needed",
                    "replicas": world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": load_traffic("single_dp_bytes"), "kernel": "kp_score_kernel + kp_dp_rows_kernel<single>, all launches of one DP (K3+K4)",
+                     "traffic": load_traffic("single_dp_bytes"), "kernel": "kp_dp_rows_kernel (fused lazy score + min-plus), all 16 wave launches of one DP",
                      "kernel_ms": dp_ms, "algorithmic_bytes_per_pattern": ALGO_BYTES_SINGLE, "peak_kind": peak_kind,
-                     "design_bytes_per_pattern": 4.0 * 3616 / 3375 * 4 + 6 * 226 / 3375.0},
+                     "design_bytes_per_pattern": 4.0 * 3616 / 3375 * (1 + 16.7) + 2 * 226 / 3375.0},
         "e2e": {"value": world * npat / (e2e_ms / 1e3), "unit": "patterns/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(codes.nbytes + pos_p.nbytes + neg_p.nbytes),
                 "d2h_bytes_per_step": int(4 + 8 * len(patnums) + 16)},
@@ -369,7 +369,7 @@ def main():
                        "nfolds": CV_FOLDS, "l2": "train/test table 20.6 GB per job >> 126 MB L2, no flush needed"},
             "roofline": {"bound": "hbm", "achieved": cvres["achieved_gbs_per_gpu"], "peak": cvres["peak"], "unit": "GB/s",
                          "frac": cvres["frac_per_gpu"], "traffic": load_traffic("cv_job_bytes"),
-                         "kernel": "kp_score_kernel<cv> + kp_dp_rows_kernel<cv>, per GPU", "algorithmic_bytes_per_pattern": ALGO_BYTES_CV,
+                         "kernel": "kp_dp_rows_kernel on train counts + backtrack/leaf kernels, per GPU", "algorithmic_bytes_per_pattern": ALGO_BYTES_CV,
                          "peak_kind": cvres["peak_kind"]},
             "e2e": {"value": cvres["pattern_scores_per_s"], "unit": "patterns/s", "h2d_bytes_per_step": int(65536 * 8 * 3 * 6),
                     "d2h_bytes_per_step": int(8 * cvres["jobs"]),

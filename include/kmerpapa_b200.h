@@ -15,6 +15,7 @@
  *   kp_backtrack       bottum_up_array_w_numba.py:8-24 (DFS, c1 subtree first)
  *   kp_split_codes     the backtrack_mem entry of bottum_up_array_w_numba.py:48-49, :64
  *   kp_dp_cv_job       bottum_up_array_penalty_plus_pseudo_CV.py:15-78,145-157, one fold per call
+ *   kp_cv_heldout      the test_score_mem entry of ..._CV.py:46-51, :71-78
  *   kp_pattern_counts  src/kmerpapa/pattern_utils.py:192-215 (get_M_U, used by cli.py:281-283)
  *
  * Conventions
@@ -95,11 +96,11 @@ int kp_dp_single(kp_plan *plan, const int64_t *d_expM, const int64_t *d_expU, ui
                  double beta, double penalty, float *d_best, uint16_t *d_kept, void *stream);
 
 /*
- * K5.  Partition of the general pattern, dense pattern numbers in the reference's emission order.
- * d_ws: device workspace of kp_backtrack_ws_bytes(cap).  Synchronises `stream`.
+ * K5.  Optimal partition of pattern `root` (UINT64_MAX: the general pattern), dense pattern numbers in the
+ * reference's emission order.  d_ws: device workspace of kp_backtrack_ws_bytes(cap).  Synchronises `stream`.
  */
 uint64_t kp_backtrack_ws_bytes(uint64_t cap);
-int kp_backtrack(kp_plan *plan, const float *d_best, const uint16_t *d_kept, void *d_ws, uint64_t cap,
+int kp_backtrack(kp_plan *plan, const float *d_best, const uint16_t *d_kept, void *d_ws, uint64_t cap, uint64_t root,
                  uint64_t *h_patnums, uint64_t *n_out, void *stream);
 
 /*
@@ -115,16 +116,27 @@ int kp_gather_table(kp_plan *plan, const float *d_table, uint64_t first, uint64_
 int kp_gather_kept(kp_plan *plan, const uint16_t *d_kept, uint64_t first, uint64_t n, uint8_t *h_out, void *stream);
 
 /*
- * One cross-validation job = one fold x alpha x penalty.  d_exp?tot: all-fold totals, d_exp?test: the
- * fold's held-out counts (both from kp_expand_counts); train counts are formed on device as
- * total - held-out.  d_train, d_test: float32[table_elems] each: training loss of the best partition of
- * every pattern and the held-out loss of that same partition.
- * h_top[2]: train and held-out loss of the general pattern (written after synchronising `stream`);
- * may be NULL to leave the result on the device and not synchronise.
+ * One cross-validation job = one fold x alpha x penalty.  d_exp?tot: all-fold totals, d_exp?test: the fold's
+ * held-out counts (both from kp_expand_counts).  Train counts are formed on the device as total - held-out into
+ * the workspace tables d_exp?tr (int64[expanded_elems]); the DP of kp_dp_single then runs on them and fills
+ * d_train (float32[table_elems]) and d_kept.  The reference additionally carries the held-out loss of every
+ * pattern's best partition but only reads it at the general pattern: that number is the float32 sum, in tree
+ * order, of the held-out losses of the leaves of the optimal partition, and is computed here from the
+ * backtracked tree (d_ws/cap as for kp_backtrack).
+ * h_top[2]: train and held-out loss of the general pattern (synchronises); NULL: DP only, no synchronisation.
  */
 int kp_dp_cv_job(kp_plan *plan, const int64_t *d_expMtot, const int64_t *d_expUtot, const int64_t *d_expMtest,
                  const int64_t *d_expUtest, uint64_t max_count, double alpha, double beta_fold, double penalty,
-                 float *d_train, float *d_test, float *h_top, void *stream);
+                 int64_t *d_expMtr, int64_t *d_expUtr, float *d_train, uint16_t *d_kept, void *d_ws, uint64_t cap,
+                 float *h_top, void *stream);
+
+/*
+ * Held-out loss of the best partition of pattern `root` after kp_dp_cv_job (the reference's test_score_mem[root],
+ * bottum_up_array_penalty_plus_pseudo_CV.py:46-51, :71-78).  Synchronises.
+ */
+int kp_cv_heldout(kp_plan *plan, const float *d_train, const uint16_t *d_kept, const int64_t *d_expMtr,
+                  const int64_t *d_expUtr, const int64_t *d_expMtest, const int64_t *d_expUtest, double alpha,
+                  double beta_fold, double penalty, uint64_t root, void *d_ws, uint64_t cap, float *h_test, void *stream);
 
 /* Counts of arbitrary patterns (dense numbers) straight from the k-mer tables.  Synchronises. */
 int kp_pattern_counts(kp_plan *plan, const int64_t *d_kmerM, const int64_t *d_kmerU, const uint64_t *h_patnums,

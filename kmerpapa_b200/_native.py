@@ -36,11 +36,12 @@ SYMBOLS = {
     "kp_expand_counts": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "kp_dp_single": (_int, [_vp, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
     "kp_backtrack_ws_bytes": (_u64, [_u64]),
-    "kp_backtrack": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, ctypes.POINTER(_u64), _vp]),
+    "kp_backtrack": (_int, [_vp, _vp, _vp, _vp, _u64, _u64, _vp, ctypes.POINTER(_u64), _vp]),
     "kp_split_codes": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp]),
     "kp_gather_table": (_int, [_vp, _vp, _u64, _u64, _vp, _vp]),
     "kp_gather_kept": (_int, [_vp, _vp, _u64, _u64, _vp, _vp]),
-    "kp_dp_cv_job": (_int, [_vp, _vp, _vp, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp]),
+    "kp_dp_cv_job": (_int, [_vp, _vp, _vp, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp]),
+    "kp_cv_heldout": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _u64, _vp, _u64, _vp, _vp]),
     "kp_pattern_counts": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp]),
     "kp_pattern_offset": (_int, [_vp, _u64, ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(ctypes.c_uint32)]),
     "kp_plan_launch_count": (_u64, [_vp]),

@@ -43,31 +43,43 @@ struct kp_plan {
     unsigned char *d_scratch = nullptr;  // staging for the small host<->device exchanges (grown on demand)
     size_t scratch_cap = 0;
     uint64_t launches = 0;
-    int nwarps[2][2] = {{0, 0}, {0, 0}};  // warps (= tiles in flight) per CTA of the DP kernel [cv][wide]
+    int nwarps[2] = {0, 0};  // warps (= tiles in flight) per CTA of the DP kernel [wide]
     size_t smem_optin = 0;
 };
 
-template <bool CV, bool WIDE>
+template <bool WIDE>
 static const void *dp_kernel_for_radix(int r0)
 {
     switch (r0) {
-    case 1: return (const void *)kp_dp_rows_kernel<1, CV, WIDE>;
-    case 3: return (const void *)kp_dp_rows_kernel<3, CV, WIDE>;
-    case 7: return (const void *)kp_dp_rows_kernel<7, CV, WIDE>;
-    default: return (const void *)kp_dp_rows_kernel<15, CV, WIDE>;
+    case 1: return (const void *)kp_dp_rows_kernel<1, WIDE>;
+    case 3: return (const void *)kp_dp_rows_kernel<3, WIDE>;
+    case 7: return (const void *)kp_dp_rows_kernel<7, WIDE>;
+    default: return (const void *)kp_dp_rows_kernel<15, WIDE>;
     }
 }
 
 template <int R0>
-static void launch_dp_r0(bool cv, bool wide, int grid, int threads, size_t smem, cudaStream_t st, const KpDpParams &prm)
+static void launch_dp_r0(bool wide, int grid, int threads, size_t smem, cudaStream_t st, const KpDpParams &prm)
 {
-    if (!cv) {
-        if (wide) kp_dp_rows_kernel<R0, false, true><<<grid, threads, smem, st>>>(prm);
-        else kp_dp_rows_kernel<R0, false, false><<<grid, threads, smem, st>>>(prm);
-    } else {
-        if (wide) kp_dp_rows_kernel<R0, true, true><<<grid, threads, smem, st>>>(prm);
-        else kp_dp_rows_kernel<R0, true, false><<<grid, threads, smem, st>>>(prm);
+    if (wide) kp_dp_rows_kernel<R0, true><<<grid, threads, smem, st>>>(prm);
+    else kp_dp_rows_kernel<R0, false><<<grid, threads, smem, st>>>(prm);
+}
+
+// float32 sum of the leaves' held-out losses in the order of the partition tree (keys sorted ascending;
+// bit 63-depth of a key tells the side taken at that depth)
+static float tree_sum(const unsigned long long *keys, const float *vals, size_t lo, size_t hi, int depth)
+{
+    if (hi - lo == 1) return vals[lo];
+    const unsigned long long bit = 1ULL << (63 - depth);
+    size_t a = lo, b = hi;  // first index whose key has the bit set
+    while (a < b) {
+        size_t mid = (a + b) / 2;
+        if (keys[mid] & bit) b = mid; else a = mid + 1;
     }
+    if (a == lo || a == hi) return tree_sum(keys, vals, lo, hi, depth + 1);  // cannot happen for a well-formed tree
+    volatile float l = tree_sum(keys, vals, lo, a, depth + 1), r = tree_sum(keys, vals, a, hi, depth + 1);
+    volatile float sum = l + r;   // float32 add, like the reference's test_score_mem row sums
+    return sum;
 }
 
 extern "C" {
@@ -75,11 +87,7 @@ extern "C" {
 const char *kp_last_error(void) { return g_err.c_str(); }
 int kp_version(void) { return 100; }
 
-static const void *dp_kernel_ptr(int r0, bool cv, bool wide)
-{
-    if (!cv) return wide ? dp_kernel_for_radix<false, true>(r0) : dp_kernel_for_radix<false, false>(r0);
-    return wide ? dp_kernel_for_radix<true, true>(r0) : dp_kernel_for_radix<true, false>(r0);
-}
+static const void *dp_kernel_ptr(int r0, bool wide) { return wide ? dp_kernel_for_radix<true>(r0) : dp_kernel_for_radix<false>(r0); }
 
 int kp_plan_create(const char *gen_pat, int device, kp_plan **out)
 {
@@ -110,17 +118,15 @@ int kp_plan_create(const char *gen_pat, int device, kp_plan **out)
     KP_CUDA(cudaMemset(p->d_err, 0, sizeof(int)));
     KP_CUDA(cudaMalloc(&p->d_counters, sizeof(uint32_t) * 64));
     p->smem_optin = prop.sharedMemPerBlockOptin;
-    for (int cv = 0; cv < 2; cv++)
-        for (int wide = 0; wide < 2; wide++) {
-            size_t fixed = 2048 + t.rt_bytes, per_warp = t.warp_smem_bytes[cv][wide];
-            int nw = fixed < p->smem_optin ? (int)((p->smem_optin - fixed) / per_warp) : 0;
-            int cap = cv ? KP_MAX_WARPS_CV : KP_MAX_WARPS;
-            if (nw > cap) nw = cap;
-            p->nwarps[cv][wide] = nw;
-            // the attribute is per function, not per plan: always raise it to the device maximum
-            KP_CUDA(cudaFuncSetAttribute(dp_kernel_ptr(t.r0, cv, wide), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)prop.sharedMemPerBlockOptin));
-        }
+    for (int wide = 0; wide < 2; wide++) {
+        size_t fixed = 2048 + t.rt_bytes, per_warp = t.warp_smem_bytes[wide];
+        int nw = fixed < p->smem_optin ? (int)((p->smem_optin - fixed) / per_warp) : 0;
+        if (nw > KP_MAX_WARPS) nw = KP_MAX_WARPS;
+        p->nwarps[wide] = nw;
+        // the attribute is per function, not per plan: always raise it to the device maximum
+        KP_CUDA(cudaFuncSetAttribute(dp_kernel_ptr(t.r0, wide), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)prop.sharedMemPerBlockOptin));
+    }
     *out = p;
     return 0;
 }
@@ -140,7 +146,7 @@ int kp_plan_destroy(kp_plan *p)
     return 0;
 }
 
-uint64_t kp_backtrack_ws_bytes(uint64_t cap) { return (3 * cap) * sizeof(KpBtNode) + cap * 8 + 80 * 8; }
+uint64_t kp_backtrack_ws_bytes(uint64_t cap) { return (3 * cap) * sizeof(KpBtNode) + cap * (8 + 8 + 4) + 80 * 8 + 64; }
 
 int kp_plan_get_info(const kp_plan *p, kp_plan_info *o)
 {
@@ -163,7 +169,7 @@ int kp_plan_get_info(const kp_plan *p, kp_plan_info *o)
     o->register_radix = (uint32_t)t.r0;
     o->rows = (uint32_t)t.nrows;
     o->rounds = (uint32_t)t.nrounds;
-    o->warps_per_cta = (uint32_t)p->nwarps[0][0];
+    o->warps_per_cta = (uint32_t)p->nwarps[0];
     o->high_levels = (uint32_t)(p->host.hl_off.size() - 1);
     o->sm_count = (uint32_t)p->sm_count;
     return 0;
@@ -254,9 +260,9 @@ int kp_expand_counts(kp_plan *p, const int64_t *d_kmerM, const int64_t *d_kmerU,
     return 0;
 }
 
-static int launch_dp(kp_plan *p, bool cv, bool wide, KpDpParams prm, cudaStream_t st)
+static int launch_dp(kp_plan *p, bool wide, KpDpParams prm, cudaStream_t st)
 {
-    int nw = p->nwarps[cv][wide];
+    int nw = p->nwarps[wide];
     if (nw < 1) return fail("DP kernel does not fit in shared memory for this tile shape");
     size_t nhl = p->host.hl_off.size() - 1;
     const KpTables &t = p->host.t;
@@ -277,12 +283,12 @@ static int launch_dp(kp_plan *p, bool cv, bool wide, KpDpParams prm, cudaStream_
         }
         uint64_t grid = (ntile + warps - 1) / warps;
         if (grid > (uint64_t)p->sm_count) grid = p->sm_count;
-        size_t sm = 2048 + t.rt_bytes + (size_t)warps * t.warp_smem_bytes[cv][wide];
+        size_t sm = 2048 + t.rt_bytes + (size_t)warps * t.warp_smem_bytes[wide];
         switch (t.r0) {
-        case 1: launch_dp_r0<1>(cv, wide, (int)grid, warps * 32, sm, st, prm); break;
-        case 3: launch_dp_r0<3>(cv, wide, (int)grid, warps * 32, sm, st, prm); break;
-        case 7: launch_dp_r0<7>(cv, wide, (int)grid, warps * 32, sm, st, prm); break;
-        default: launch_dp_r0<15>(cv, wide, (int)grid, warps * 32, sm, st, prm); break;
+        case 1: launch_dp_r0<1>(wide, (int)grid, warps * 32, sm, st, prm); break;
+        case 3: launch_dp_r0<3>(wide, (int)grid, warps * 32, sm, st, prm); break;
+        case 7: launch_dp_r0<7>(wide, (int)grid, warps * 32, sm, st, prm); break;
+        default: launch_dp_r0<15>(wide, (int)grid, warps * 32, sm, st, prm); break;
         }
         p->launches++;
     }
@@ -305,51 +311,20 @@ int kp_dp_single(kp_plan *p, const int64_t *d_expM, const int64_t *d_expU, uint6
     prm.alpha = alpha; prm.beta = beta; prm.penalty = penalty;
     prm.best = d_best;
     prm.flags = d_kept;
-    return launch_dp(p, false, wide, prm, (cudaStream_t)stream);
+    return launch_dp(p, wide, prm, (cudaStream_t)stream);
 }
 
-int kp_dp_cv_job(kp_plan *p, const int64_t *d_expMtot, const int64_t *d_expUtot, const int64_t *d_expMtest,
-                 const int64_t *d_expUtest, uint64_t max_count, double alpha, double beta_fold, double penalty,
-                 float *d_train, float *d_test, float *h_top, void *stream)
+// breadth-first backtrack from `root`; leaves end up sorted by path key in the workspace
+static int backtrack_device(kp_plan *p, const float *d_best, const uint16_t *d_kept, void *d_ws, uint64_t cap, uint64_t root,
+                            cudaStream_t st, unsigned long long **sorted_out, unsigned long long **keys_out, float **vals_out,
+                            unsigned long long **ctr_out)
 {
-    if (!p) return fail("kp_dp_cv_job: null plan");
-    KP_CUDA(cudaSetDevice(p->device));
-    bool wide = max_count > 0xFFFFFFFFull;
-    KpDpParams prm;
-    memset(&prm, 0, sizeof prm);
-    prm.tab = p->d_tab;
-    prm.rowtab = p->d_rowtab;
-    prm.e0 = (const long long *)d_expMtot;
-    prm.e1 = (const long long *)d_expUtot;
-    prm.e2 = (const long long *)d_expMtest;
-    prm.e3 = (const long long *)d_expUtest;
-    prm.alpha = alpha; prm.beta = beta_fold; prm.penalty = penalty;
-    prm.best = d_train;
-    prm.test = d_test;
-    if (launch_dp(p, true, wide, prm, (cudaStream_t)stream)) return 1;
-    if (h_top) {
-        uint64_t tile; uint32_t srow, d0;
-        kp_locate(p->host, p->host.npat - 1, &tile, &srow, &d0);
-        const KpTables &t = p->host.t;
-        size_t top = (size_t)tile * t.tile_stride + ((size_t)(d0 >> 2) * t.rp + srow) * 4 + (d0 & 3);
-        KP_CUDA(cudaMemcpyAsync(h_top, d_train + top, sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-        KP_CUDA(cudaMemcpyAsync(h_top + 1, d_test + top, sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-        KP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-    }
-    return 0;
-}
-
-int kp_backtrack(kp_plan *p, const float *d_best, const uint16_t *d_kept, void *d_ws, uint64_t cap, uint64_t *h_patnums,
-                 uint64_t *n_out, void *stream)
-{
-    if (!p || !d_ws || !h_patnums || !n_out) return fail("kp_backtrack: null argument");
-    if (p->host.t.total_level > 64) return fail("kp_backtrack: more than 64 levels");
-    cudaStream_t st = (cudaStream_t)stream;
-    KP_CUDA(cudaSetDevice(p->device));
     KpBtNode *fa = (KpBtNode *)d_ws, *fb = fa + cap, *leaves = fb + cap;
     unsigned long long *sorted = (unsigned long long *)(leaves + cap);
-    unsigned long long *ctr = sorted + cap;   // [0] leaves, [1] overflow, [2 + d] nodes at depth d
-    kp_backtrack_init_kernel<<<1, 128, 0, st>>>(fa, p->host.npat - 1, ctr);
+    unsigned long long *keys = sorted + cap;
+    unsigned long long *ctr = keys + cap;   // [0] leaves, [1] overflow, [2 + d] nodes at depth d
+    float *vals = (float *)(ctr + 80);
+    kp_backtrack_init_kernel<<<1, 128, 0, st>>>(fa, root, ctr);
     const int levels = (int)p->host.t.total_level + 1;
     int grid = (int)((cap + 7) / 8);
     if (grid > p->sm_count * 2) grid = p->sm_count * 2;
@@ -358,9 +333,25 @@ int kp_backtrack(kp_plan *p, const float *d_best, const uint16_t *d_kept, void *
                                                         (d & 1) ? fa : fb, leaves, cap, ctr);
         p->launches++;
     }
-    kp_backtrack_sort_kernel<<<p->sm_count, 256, 0, st>>>(leaves, ctr, cap, sorted);
+    kp_backtrack_sort_kernel<<<p->sm_count, 256, 0, st>>>(leaves, ctr, cap, sorted, keys);
     p->launches += 2;
     KP_CUDA(cudaGetLastError());
+    *sorted_out = sorted; *keys_out = keys; *vals_out = vals; *ctr_out = ctr;
+    return 0;
+}
+
+int kp_backtrack(kp_plan *p, const float *d_best, const uint16_t *d_kept, void *d_ws, uint64_t cap, uint64_t root,
+                 uint64_t *h_patnums, uint64_t *n_out, void *stream)
+{
+    if (!p || !d_ws || !h_patnums || !n_out) return fail("kp_backtrack: null argument");
+    if (p->host.t.total_level > 64) return fail("kp_backtrack: more than 64 levels");
+    if (root == UINT64_MAX) root = p->host.npat - 1;
+    if (root >= p->host.npat) return fail("kp_backtrack: root out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    KP_CUDA(cudaSetDevice(p->device));
+    unsigned long long *sorted, *keys, *ctr;
+    float *vals;
+    if (backtrack_device(p, d_best, d_kept, d_ws, cap, root, st, &sorted, &keys, &vals, &ctr)) return 1;
     unsigned long long hc[2] = {0, 0};
     KP_CUDA(cudaMemcpyAsync(hc, ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaStreamSynchronize(st));
@@ -368,6 +359,66 @@ int kp_backtrack(kp_plan *p, const float *d_best, const uint16_t *d_kept, void *
     if (hc[1] || hc[0] > cap) return fail("kp_backtrack: partition larger than the workspace capacity");
     KP_CUDA(cudaMemcpyAsync(h_patnums, sorted, hc[0] * 8, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int kp_cv_heldout(kp_plan *p, const float *d_train, const uint16_t *d_kept, const int64_t *d_expMtr, const int64_t *d_expUtr,
+                  const int64_t *d_expMtest, const int64_t *d_expUtest, double alpha, double beta_fold, double penalty,
+                  uint64_t root, void *d_ws, uint64_t cap, float *h_test, void *stream)
+{
+    if (!p || !d_ws || !h_test) return fail("kp_cv_heldout: null argument");
+    if (root == UINT64_MAX) root = p->host.npat - 1;
+    if (root >= p->host.npat) return fail("kp_cv_heldout: root out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    KP_CUDA(cudaSetDevice(p->device));
+    unsigned long long *sorted, *keys, *ctr;
+    float *vals;
+    if (backtrack_device(p, d_train, d_kept, d_ws, cap, root, st, &sorted, &keys, &vals, &ctr)) return 1;
+    kp_cv_leaf_kernel<<<p->sm_count, 128, 0, st>>>(p->d_tab, p->d_rowtab, (const long long *)d_expMtr, (const long long *)d_expUtr,
+                                                   (const long long *)d_expMtest, (const long long *)d_expUtest, alpha, beta_fold,
+                                                   penalty, sorted, ctr, cap, vals);
+    p->launches++;
+    KP_CUDA(cudaGetLastError());
+    unsigned long long hc[2] = {0, 0};
+    KP_CUDA(cudaMemcpyAsync(hc, ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    if (hc[1] || hc[0] > cap || hc[0] == 0) return fail("kp_cv_heldout: partition larger than the workspace capacity");
+    std::vector<unsigned long long> hk(hc[0]);
+    std::vector<float> hv(hc[0]);
+    KP_CUDA(cudaMemcpyAsync(hk.data(), keys, hc[0] * 8, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaMemcpyAsync(hv.data(), vals, hc[0] * 4, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    *h_test = tree_sum(hk.data(), hv.data(), 0, hc[0], 0);
+    return 0;
+}
+
+int kp_dp_cv_job(kp_plan *p, const int64_t *d_expMtot, const int64_t *d_expUtot, const int64_t *d_expMtest,
+                 const int64_t *d_expUtest, uint64_t max_count, double alpha, double beta_fold, double penalty,
+                 int64_t *d_expMtr, int64_t *d_expUtr, float *d_train, uint16_t *d_kept, void *d_ws, uint64_t cap,
+                 float *h_top, void *stream)
+{
+    if (!p) return fail("kp_dp_cv_job: null plan");
+    cudaStream_t st = (cudaStream_t)stream;
+    KP_CUDA(cudaSetDevice(p->device));
+    const KpTables &t = p->host.t;
+    const uint64_t nexp = (uint64_t)t.ntiles * t.tile_kmers;
+    // train counts = total - held-out, on the expanded tables (sums commute with the subtraction)
+    kp_train_counts_kernel<<<grid_for(nexp, 256, p->sm_count), 256, 0, st>>>((const long long *)d_expMtot, (const long long *)d_expMtest,
+                                                                             (long long *)d_expMtr, nexp);
+    kp_train_counts_kernel<<<grid_for(nexp, 256, p->sm_count), 256, 0, st>>>((const long long *)d_expUtot, (const long long *)d_expUtest,
+                                                                             (long long *)d_expUtr, nexp);
+    p->launches += 2;
+    if (kp_dp_single(p, d_expMtr, d_expUtr, max_count, alpha, beta_fold, penalty, d_train, d_kept, stream)) return 1;
+    if (h_top) {
+        if (kp_cv_heldout(p, d_train, d_kept, d_expMtr, d_expUtr, d_expMtest, d_expUtest, alpha, beta_fold, penalty, UINT64_MAX,
+                          d_ws, cap, h_top + 1, stream))
+            return 1;
+        uint64_t tile; uint32_t srow, d0;
+        kp_locate(p->host, p->host.npat - 1, &tile, &srow, &d0);
+        size_t top = (size_t)tile * t.tile_stride + ((size_t)(d0 >> 2) * t.rp + srow) * 4 + (d0 & 3);
+        KP_CUDA(cudaMemcpyAsync(h_top, d_train + top, sizeof(float), cudaMemcpyDeviceToHost, st));
+        KP_CUDA(cudaStreamSynchronize(st));
+    }
     return 0;
 }
 

@@ -8,8 +8,7 @@
 //      Per tile:
 //        phase D  (single DP) stream the two child tiles of every HIGH-position split for all rows, 32
 //                 consecutive rows at a time, coalesced 16-byte loads, one flattened two-deep software
-//                 pipeline; the running minimum of each row is parked in shared memory.  (The CV job
-//                 streams inside the rounds because it also has to track which split won.)
+//                 pipeline; the running minimum of each row is parked in shared memory.
 //        rounds   rows are visited in a precomputed schedule (<= 32 rows whose children are complete):
 //                 running minimum over the CROSS-row splits from the tile's finished rows in shared memory;
 //                 counts of the row from the tile's base k-mers by subset sums;
@@ -23,9 +22,13 @@
 //                 sf < best || (sf == best && rounded_up), and the value it stores on a win is sf;
 //                 in-register splits of the register position interleaved with that compare, fully
 //                 unrolled; one coalesced 16-byte store per group, one 16-bit "kept whole" mask per row.
-//      The single DP only keeps the minimum (fminf); which split won is re-derived by the backtrack from
-//      the stored scores (first split in scan order that reproduces the minimum).  The CV job needs the
-//      held-out loss of the winning split, so it tracks (value, scan rank) lexicographically.
+//      The kernel only keeps the minimum (fminf); which split won is re-derived by the backtrack from the
+//      stored scores (first split in scan order that reproduces the minimum).
+//
+//  CV job = the same kernel on the TRAIN counts (total - held-out).  The reference also carries the held-out
+//      loss of every pattern's best partition, but only reads it at the general pattern; that value is the
+//      float32 sum, along the optimal partition tree, of the leaves' held-out losses, so it is computed
+//      after the DP from the backtracked tree (kp_cv_leaf_kernel + a host reduction in tree order).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -33,8 +36,7 @@
 #include "kp_math.cuh"
 #include "kp_tables.h"
 
-#define KP_MAX_WARPS 14      // single DP: tiles in flight per SM (<= 128 registers per thread)
-#define KP_MAX_WARPS_CV 12   // CV job: fewer warps, up to 168 registers per thread (winner codes + held-out values)
+#define KP_MAX_WARPS 14      // tiles in flight per SM (<= 128 registers per thread)
 
 template <bool WIDE> struct KpCnt { typedef unsigned int type; };
 template <> struct KpCnt<true> { typedef unsigned long long type; };
@@ -142,60 +144,23 @@ struct KpDpParams {
     uint32_t ntiles_wave;
     uint32_t *counter;          // next unclaimed entry of tile_list (zeroed before the launch)
     int leaf_wave;              // wave 0: rows of level 0 hold k-mers at the single-nucleotide digits
-    const long long *e0, *e1, *e2, *e3;  // single: M, U.  CV: Mtot, Utot, Mtest, Utest  [ntiles][tile_kmers]
+    const long long *e0, *e1;   // expanded counts M, U  [ntiles][tile_kmers]
     double alpha, beta, penalty;
-    float *best;        // single: best loss;  CV: train loss
-    float *test;        // CV: held-out loss of the chosen partition
-    uint16_t *flags;    // single: per row, bit d set = pattern kept whole
+    float *best;                // best loss per pattern
+    uint16_t *flags;            // per row, bit d set = pattern kept whole
 };
 
-// CV winner code: (scan rank = position*8 + j) << 8 | where.  where = index into the tile's high-split list,
-// 0x80 | index into the row's cross-row list, or 0xFF for an in-register split (its held-out loss is at hand).
-// Codes order like scan ranks, so (value, code) compared lexicographically picks the reference's winner.
-#define KP_NONE 0x7fffffff
-#define KP_INROW 0xFF
-
-template <int R0, bool CV>
-struct KpRow {
-    static constexpr int NG = (R0 + 3) / 4;
-    float v[NG * 4];             // best (train) loss so far / final
-    float tv[CV ? NG * 4 : 1];   // CV: held-out loss of the current winner
-    int rk[CV ? NG * 4 : 1];     // CV: code of the current winner, KP_NONE = none yet
-    uint32_t need, rup, flag;    // per digit: exact self-score available / it rounded up / kept whole
-};
-
-template <int R0, bool CV>
-struct KpRowOps {
-    typedef KpRow<R0, CV> Row;
-    // one in-register split candidate of digit D with children A, B (J = split index in scan order)
-    template <int D, int A, int B, int J>
-    static __device__ __forceinline__ void split(Row &r, int rankbase)
-    {
-        float cand = __fadd_rn(r.v[A], r.v[B]);
-        if (!CV) {
-            r.v[D] = fminf(r.v[D], cand);
-        } else {
-            int code = ((rankbase + J) << 8) | KP_INROW;
-            bool take = (cand < r.v[D]) || (cand == r.v[D] && code < r.rk[D]);
-            if (take) { r.v[D] = cand; r.rk[D] = code; r.tv[D] = __fadd_rn(r.tv[A], r.tv[B]); }
-        }
-    }
-};
-
-template <int R0, bool CV, bool WIDE>
-__global__ void __launch_bounds__((CV ? KP_MAX_WARPS_CV : KP_MAX_WARPS) * 32, 1) kp_dp_rows_kernel(const KpDpParams p)
+template <int R0, bool WIDE>
+__global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const KpDpParams p)
 {
-    typedef KpRow<R0, CV> Row;
-    typedef KpRowOps<R0, CV> Ops;
     typedef typename KpCnt<WIDE>::type C;
-    constexpr int NG = Row::NG;
+    constexpr int NG = (R0 + 3) / 4;
     constexpr int NB = R0 == 15 ? 4 : (R0 == 7 ? 3 : (R0 == 3 ? 2 : 1));
-    constexpr int CW = CV ? 4 : 2;  // counters per base k-mer
 
     extern __shared__ __align__(16) unsigned char smem[];
     const KpTables &tb = *p.tab;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int rp = tb.rp, nrounds = tb.nrounds, nhigh = tb.nhigh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rp = tb.rp, nrounds = tb.nrounds, nhigh = tb.nhigh, nrows = tb.nrows;
     const uint32_t stride = tb.tile_stride, tk = tb.tile_kmers;
     const uint32_t rt_bytes = tb.rt_bytes;
     const int maxhs = tb.maxhs;
@@ -209,34 +174,30 @@ __global__ void __launch_bounds__((CV ? KP_MAX_WARPS_CV : KP_MAX_WARPS) * 32, 1)
     const uint8_t *row_level = rt + tb.rt_row_level;
     const uint16_t *xs_off = (const uint16_t *)(rt + tb.rt_xs_off);
     const uint32_t *xs = (const uint32_t *)(rt + tb.rt_xs);
-    const uint8_t *xsr = rt + tb.rt_xs_rank;
     const uint16_t *bs_off = (const uint16_t *)(rt + tb.rt_bs_off);
     const uint16_t *bs = (const uint16_t *)(rt + tb.rt_bs);
 
-    unsigned char *wm = smem + 2048 + rt_bytes + (size_t)warp * tb.warp_smem_bytes[CV][WIDE];
-    float4 *S = (float4 *)wm;                                  // [NG][rp]
-    C *bc = (C *)(wm + (size_t)NG * rp * 16);                  // [tile_kmers][CW] base counts of the tile
-    uint32_t *hs1 = (uint32_t *)((unsigned char *)bc + (size_t)tk * CW * sizeof(C));
+    unsigned char *wm = smem + 2048 + rt_bytes + (size_t)warp * tb.warp_smem_bytes[WIDE];
+    float4 *S = (float4 *)wm;                                  // [NG][rp] the warp's copy of its tile
+    C *bc = (C *)(wm + (size_t)NG * rp * 16);                  // [tile_kmers][2] base counts of the tile
+    uint32_t *hs1 = (uint32_t *)((unsigned char *)bc + (size_t)tk * 2 * sizeof(C));
     uint32_t *hs2 = hs1 + maxhs;
-    uint8_t *hsr = (uint8_t *)(hs2 + maxhs);
-    int *s_nhs = (int *)(hsr + ((maxhs + 3) & ~3));
+    int *s_nhs = (int *)(hs2 + maxhs);
     const double alpha = p.alpha, beta = p.beta, penalty = p.penalty;
     const float alpha_f = (float)alpha, ab_f = (float)(alpha + beta), penalty_f = (float)penalty;
-
     const float INF = __int_as_float(0x7f800000);
-    const int rankbase = tb.estar >= 0 ? tb.pos_id[tb.estar] * 8 : 0;
+    const float *tbase = p.best;
 
     // Tiles are claimed in list order (ascending tile number): the tiles in flight on the whole GPU are then
     // always neighbours in the pattern lattice, which share child tiles, so those re-reads hit in L2.
-    (void)nwarps;
     for (;;) {
         uint32_t it = 0;
         if (lane == 0) it = atomicAdd(p.counter, 1u);
         it = __shfl_sync(0xffffffffu, it, 0);
         if (it >= p.ntiles_wave) break;
         const uint32_t tile = p.tile_list[it];
-        __syncwarp();  // previous tile's readers of S / hs are done
-        // ---- the tile's high-position splits, in scan order ----
+        __syncwarp();  // previous tile's readers of S / bc / hs are done
+        // ---- the tile's high-position splits (two child tiles each) ----
         {
             int ns = 0, d = 0, e = 0;
             uint32_t m = 0, hw = 1;
@@ -259,77 +220,27 @@ __global__ void __launch_bounds__((CV ? KP_MAX_WARPS_CV : KP_MAX_WARPS) * 32, 1)
                 int c1 = tb.mask_digit[e][tb.ms_c1[m][j]], c2 = tb.mask_digit[e][tb.ms_c2[m][j]];
                 hs1[off + j] = tile - (uint32_t)(d - c1) * hw;
                 hs2[off + j] = tile - (uint32_t)(d - c2) * hw;
-                hsr[off + j] = (uint8_t)(tb.pos_id[e] * 8 + j);
             }
             if (lane == 0) *s_nhs = total;
         }
         // ---- base counts of the tile ----
         for (uint32_t kl = lane; kl < tk; kl += 32) {
             size_t g = (size_t)tile * tk + kl;
-            if (!CV) {
-                bc[kl * CW + 0] = (C)p.e0[g];
-                bc[kl * CW + 1] = (C)p.e1[g];
-            } else {
-                long long mt = p.e2[g], ut = p.e3[g];
-                bc[kl * CW + 0] = (C)(p.e0[g] - mt);  // train = total - held-out
-                bc[kl * CW + 1] = (C)(p.e1[g] - ut);
-                bc[kl * CW + 2] = (C)mt;
-                bc[kl * CW + 3] = (C)ut;
-            }
+            bc[kl * 2 + 0] = (C)p.e0[g];
+            bc[kl * 2 + 1] = (C)p.e1[g];
         }
         __syncwarp();
         const int nhs = *s_nhs;
-        const float *tbase = p.best;
         float4 *otile = (float4 *)(p.best + (size_t)tile * stride);
 
-        // ---- phase D (single DP): stream the child tiles of the high-position splits for ALL rows of the tile,
-        //      32 consecutive rows at a time, two splits in flight; the running minimum of row r is parked
-        //      in S[r] until the row's turn in the schedule ----
-#define KP_HS_LOAD(s, xa, xb)                                                                        \
-    {                                                                                                \
-        const float4 *a_ = (const float4 *)(tbase + (size_t)hs1[s] * stride) + srow;                 \
-        const float4 *b_ = (const float4 *)(tbase + (size_t)hs2[s] * stride) + srow;                 \
-        _Pragma("unroll") for (int g = 0; g < NG; g++) { xa[g] = __ldg(a_ + g * rp); xb[g] = __ldg(b_ + g * rp); } \
-    }
-#define KP_HS_USE(s, xa, xb)                                                                         \
-    {                                                                                                \
-        const int code = CV ? (((int)hsr[s] << 8) | (s)) : 0;                                        \
-        _Pragma("unroll") for (int g = 0; g < NG; g++) {                                             \
-            float c0 = __fadd_rn(xa[g].x, xb[g].x), c1 = __fadd_rn(xa[g].y, xb[g].y);                \
-            float c2 = __fadd_rn(xa[g].z, xb[g].z), c3 = __fadd_rn(xa[g].w, xb[g].w);                \
-            if (!CV) {                                                                               \
-                r.v[4 * g + 0] = fminf(r.v[4 * g + 0], c0);                                          \
-                r.v[4 * g + 1] = fminf(r.v[4 * g + 1], c1);                                          \
-                r.v[4 * g + 2] = fminf(r.v[4 * g + 2], c2);                                          \
-                r.v[4 * g + 3] = fminf(r.v[4 * g + 3], c3);                                          \
-            } else { /* hs is in scan order: a strict '<' keeps the earliest split among equals */   \
-                if (c0 < r.v[4 * g + 0]) { r.v[4 * g + 0] = c0; r.rk[4 * g + 0] = code; }           \
-                if (c1 < r.v[4 * g + 1]) { r.v[4 * g + 1] = c1; r.rk[4 * g + 1] = code; }           \
-                if (c2 < r.v[4 * g + 2]) { r.v[4 * g + 2] = c2; r.rk[4 * g + 2] = code; }           \
-                if (c3 < r.v[4 * g + 3]) { r.v[4 * g + 3] = c3; r.rk[4 * g + 3] = code; }           \
-            }                                                                                        \
-        }                                                                                            \
-    }
-#define KP_HS_STREAM()                                                                               \
-    {                                                                                                \
-        float4 xa0[NG], xb0[NG], xa1[NG], xb1[NG];                                                   \
-        int s = 0;                                                                                   \
-        if (nhs > 0) KP_HS_LOAD(0, xa0, xb0)                                                         \
-        for (; s + 2 <= nhs; s += 2) {                                                               \
-            KP_HS_LOAD(s + 1, xa1, xb1)                                                              \
-            KP_HS_USE(s, xa0, xb0)                                                                   \
-            if (s + 2 < nhs) KP_HS_LOAD(s + 2, xa0, xb0)                                             \
-            KP_HS_USE(s + 1, xa1, xb1)                                                               \
-        }                                                                                            \
-        if (s < nhs) KP_HS_USE(s, xa0, xb0)                                                          \
-    }
-        if (!CV) {
-            // one flattened software pipeline over (32-row chunk, split): a load is always two steps ahead of
-            // its use, also across chunk boundaries, so the pipeline drains once per tile, not once per chunk
-            Row r;
+        // ---- phase D: stream the child tiles of the high-position splits for ALL rows of the tile; the running
+        //      minimum of row r is parked in S[r] until the row's turn in the schedule.  One flattened software
+        //      pipeline over (32-row chunk, split): a load is always two steps ahead of its use, also across
+        //      chunk boundaries, so the pipeline drains once per tile ----
+        {
+            float v[NG * 4];
 #pragma unroll
-            for (int c = 0; c < NG * 4; c++) r.v[c] = INF;
-            const int nrows = tb.nrows;
+            for (int c = 0; c < NG * 4; c++) v[c] = INF;
             const int nchunk = (nrows + 31) >> 5;
             const int nstep = nhs > 0 ? nchunk * nhs : 0;
             float4 xa0[NG], xb0[NG], xa1[NG], xb1[NG];
@@ -346,17 +257,17 @@ __global__ void __launch_bounds__((CV ? KP_MAX_WARPS_CV : KP_MAX_WARPS) * 32, 1)
 #define KP_FL_USE(xa, xb)                                                                             \
     {                                                                                                 \
         _Pragma("unroll") for (int g = 0; g < NG; g++) {                                              \
-            r.v[4 * g + 0] = fminf(r.v[4 * g + 0], __fadd_rn(xa[g].x, xb[g].x));                      \
-            r.v[4 * g + 1] = fminf(r.v[4 * g + 1], __fadd_rn(xa[g].y, xb[g].y));                      \
-            r.v[4 * g + 2] = fminf(r.v[4 * g + 2], __fadd_rn(xa[g].z, xb[g].z));                      \
-            r.v[4 * g + 3] = fminf(r.v[4 * g + 3], __fadd_rn(xa[g].w, xb[g].w));                      \
+            v[4 * g + 0] = fminf(v[4 * g + 0], __fadd_rn(xa[g].x, xb[g].x));                          \
+            v[4 * g + 1] = fminf(v[4 * g + 1], __fadd_rn(xa[g].y, xb[g].y));                          \
+            v[4 * g + 2] = fminf(v[4 * g + 2], __fadd_rn(xa[g].z, xb[g].z));                          \
+            v[4 * g + 3] = fminf(v[4 * g + 3], __fadd_rn(xa[g].w, xb[g].w));                          \
         }                                                                                             \
         if (++us == nhs) {   /* chunk complete: park its minima, start the next chunk */              \
             if (urow < nrows) {                                                                       \
                 _Pragma("unroll") for (int g = 0; g < NG; g++)                                        \
-                    S[g * rp + urow] = make_float4(r.v[4 * g], r.v[4 * g + 1], r.v[4 * g + 2], r.v[4 * g + 3]); \
+                    S[g * rp + urow] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]); \
             }                                                                                         \
-            _Pragma("unroll") for (int c = 0; c < NG * 4; c++) r.v[c] = INF;                          \
+            _Pragma("unroll") for (int c = 0; c < NG * 4; c++) v[c] = INF;                            \
             us = 0; urow += 32;                                                                       \
         }                                                                                             \
     }
@@ -379,63 +290,39 @@ __global__ void __launch_bounds__((CV ? KP_MAX_WARPS_CV : KP_MAX_WARPS) * 32, 1)
             __syncwarp();
         }
 
+        // ---- rounds ----
         for (int rnd = 0; rnd < nrounds; rnd++) {
             const int srow = round_start[rnd] + lane;
             if (srow < round_start[rnd + 1]) {
-                Row r;
-                r.flag = 0;
+                float v[NG * 4];
 #pragma unroll
-                for (int c = 0; c < NG * 4; c++) { r.v[c] = INF; if (CV) { r.tv[c] = 0.f; r.rk[c] = KP_NONE; } }
-
-                if (CV) {
-                    // ---- high-position splits: stream two child tiles per split, two splits in flight ----
-                    KP_HS_STREAM()
-                } else {
-#pragma unroll
-                    for (int g = 0; g < NG; g++) {  // minimum over the high-position splits, parked by phase D
-                        float4 x = S[g * rp + srow];
-                        r.v[4 * g] = x.x; r.v[4 * g + 1] = x.y; r.v[4 * g + 2] = x.z; r.v[4 * g + 3] = x.w;
-                    }
+                for (int g = 0; g < NG; g++) {  // minimum over the high-position splits, parked by phase D
+                    float4 x = S[g * rp + srow];
+                    v[4 * g] = x.x; v[4 * g + 1] = x.y; v[4 * g + 2] = x.z; v[4 * g + 3] = x.w;
                 }
                 // ---- cross-row splits: finished rows of this tile, shared memory ----
                 for (int i = xs_off[srow]; i < xs_off[srow + 1]; i++) {
                     const uint32_t pr = xs[i];
                     const float4 *a = S + (pr & 0xFFFFu), *b = S + (pr >> 16);
-                    const int code = CV ? (((int)xsr[i] << 8) | 0x80 | (i - xs_off[srow])) : 0;
 #pragma unroll
                     for (int g = 0; g < NG; g++) {
                         float4 xa = a[g * rp], xb = b[g * rp];
-                        float c0 = __fadd_rn(xa.x, xb.x), c1 = __fadd_rn(xa.y, xb.y);
-                        float c2 = __fadd_rn(xa.z, xb.z), c3 = __fadd_rn(xa.w, xb.w);
-                        if (!CV) {
-                            r.v[4 * g + 0] = fminf(r.v[4 * g + 0], c0);
-                            r.v[4 * g + 1] = fminf(r.v[4 * g + 1], c1);
-                            r.v[4 * g + 2] = fminf(r.v[4 * g + 2], c2);
-                            r.v[4 * g + 3] = fminf(r.v[4 * g + 3], c3);
-                        } else {
-                            // cross-row and streamed splits interleave in scan order: compare (value, rank)
-#define KP_CVX(c, cand)                                                                                          \
-    if ((cand) < r.v[c] || ((cand) == r.v[c] && code < r.rk[c])) { r.v[c] = (cand); r.rk[c] = code; }
-                            KP_CVX(4 * g + 0, c0) KP_CVX(4 * g + 1, c1) KP_CVX(4 * g + 2, c2) KP_CVX(4 * g + 3, c3)
-#undef KP_CVX
-                        }
+                        v[4 * g + 0] = fminf(v[4 * g + 0], __fadd_rn(xa.x, xb.x));
+                        v[4 * g + 1] = fminf(v[4 * g + 1], __fadd_rn(xa.y, xb.y));
+                        v[4 * g + 2] = fminf(v[4 * g + 2], __fadd_rn(xa.z, xb.z));
+                        v[4 * g + 3] = fminf(v[4 * g + 3], __fadd_rn(xa.w, xb.w));
                     }
                 }
-
                 // ---- counts of this row at the single-nucleotide digits of the register position ----
-                C m[NB], u[NB], mt[CV ? NB : 1], ut[CV ? NB : 1];
+                C m[NB], u[NB];
 #pragma unroll
-                for (int b = 0; b < NB; b++) { m[b] = 0; u[b] = 0; if (CV) { mt[b] = 0; ut[b] = 0; } }
+                for (int b = 0; b < NB; b++) { m[b] = 0; u[b] = 0; }
                 for (int i = bs_off[srow]; i < bs_off[srow + 1]; i++) {
-                    const C *q = bc + (size_t)bs[i] * NB * CW;
+                    const C *q = bc + (size_t)bs[i] * NB * 2;
 #pragma unroll
-                    for (int b = 0; b < NB; b++) {
-                        m[b] += q[b * CW + 0];
-                        u[b] += q[b * CW + 1];
-                        if (CV) { mt[b] += q[b * CW + 2]; ut[b] += q[b * CW + 3]; }
-                    }
+                    for (int b = 0; b < NB; b++) { m[b] += q[b * 2 + 0]; u[b] += q[b * 2 + 1]; }
                 }
-                // ---- score filter: which patterns can still be kept whole? (r.v only decreases from here) ----
+                // ---- score filter: which patterns can still be kept whole? (v only decreases from here) ----
                 const bool leafrow = p.leaf_wave && row_level[srow] == 0;
                 uint32_t need = 0;
                 {
@@ -450,12 +337,12 @@ __global__ void __launch_bounds__((CV ? KP_MAX_WARPS_CV : KP_MAX_WARPS) * 32, 1)
                             if ((kp_bm_c<R0>(d) >> b) & 1) { Mf += mf[b]; Uf += uf[b]; }
                         float est = kp_score_estimate(Mf, Uf, alpha_f, ab_f, penalty_f);
                         float margin = 2e-4f * fabsf(est) + 0.01f;
-                        if (!(est - margin > r.v[d])) need |= 1u << d;
+                        if (!(est - margin > v[d])) need |= 1u << d;
                     }
                     if (leafrow) need |= (1u << NB) - 1u;
                 }
                 // ---- exact float64 self-score of the patterns that passed the filter ----
-                float sfx[NG * 4], tfx[CV ? NG * 4 : 1];   // indexed at run time below: lives in local memory, rarely touched
+                float sfx[NG * 4];   // indexed at run time below: lives in local memory, rarely touched
                 uint32_t rupm = 0;
                 if (need) {
                     const KpLogK K = kp_logk_load();
@@ -464,106 +351,81 @@ __global__ void __launch_bounds__((CV ? KP_MAX_WARPS_CV : KP_MAX_WARPS) * 32, 1)
                         const int d = __ffs(todo) - 1;
                         todo &= todo - 1;
                         const unsigned bm = kp_bm<R0>(d);
-                        C M_ = 0, U_ = 0, Mt_ = 0, Ut_ = 0;
+                        C M_ = 0, U_ = 0;
 #pragma unroll
                         for (int b = 0; b < NB; b++)
-                            if ((bm >> b) & 1u) { M_ += m[b]; U_ += u[b]; if (CV) { Mt_ += mt[b]; Ut_ += ut[b]; } }
-                        double s_, t_ = 0.0, lp_, l1_;
-                        if (leafrow && d < NB) {
-                            if (!CV) s_ = kp_leaf_score_nl(M_, U_, alpha, beta, penalty, logtab);
-                            else kp_leaf_cv_nl(M_, U_, Mt_, Ut_, alpha, beta, penalty, logtab, &s_, &t_);
-                        } else {
-                            s_ = kp_self_score_t<C>(M_, U_, alpha, beta, penalty, logtab, K, lp_, l1_);
-                            if (CV) t_ = kp_test_ll_t<C>(Mt_, Ut_, lp_, l1_);
-                        }
+                            if ((bm >> b) & 1u) { M_ += m[b]; U_ += u[b]; }
+                        double s_, lp_, l1_;
+                        if (leafrow && d < NB) s_ = kp_leaf_score_nl(M_, U_, alpha, beta, penalty, logtab);
+                        else s_ = kp_self_score_t<C>(M_, U_, alpha, beta, penalty, logtab, K, lp_, l1_);
                         const float sf = __double2float_rn(s_);
                         if ((double)sf > s_) rupm |= 1u << d;
                         sfx[d] = sf;
-                        if (CV) tfx[d] = __double2float_rn(t_);
                     }
                 }
-                r.need = need;
-                r.rup = rupm;
-
-                // ---- register position: in-register splits + self-score compare, digit by digit ----
-                // CV: fetch the held-out loss of a winner that came from memory (streamed or cross-row split)
-                auto fetch_test = [&](int d, int code) -> float {
-                    const int inrow = ((d >> 2) * rp) * 4 + (d & 3);
-                    if (code & 0x80) {  // cross-row split: rows of this tile, written by this warp in earlier rounds
-                        const uint32_t pr = xs[xs_off[srow] + (code & 0x7F)];
-                        const float *t0 = p.test + (size_t)tile * stride + inrow;
-                        return __fadd_rn(__ldcg(t0 + (pr & 0xFFFFu) * 4), __ldcg(t0 + (pr >> 16) * 4));
-                    }
-                    const int s = code & 0x7F;  // high-position split: the two child tiles, same row
-                    return __fadd_rn(__ldg(p.test + (size_t)hs1[s] * stride + inrow + srow * 4),
-                                     __ldg(p.test + (size_t)hs2[s] * stride + inrow + srow * 4));
-                };
-                // reference: if s < (double)best: best = f32(s)   <=>   sf < best || (sf == best && sf > s)
-#define KP_FIN(D)                                                                                                \
-    {                                                                                                            \
-        bool self_ = false;                                                                                      \
-        float sf_ = 0.f;                                                                                         \
-        if ((r.need >> (D)) & 1u) {                                                                              \
-            sf_ = sfx[D];                                                                                        \
-            self_ = sf_ < r.v[D] || (sf_ == r.v[D] && ((r.rup >> (D)) & 1u));                                    \
-        }                                                                                                        \
-        if (!CV) {                                                                                               \
-            if (self_) { r.v[D] = sf_; r.flag |= 1u << (D); }                                                    \
-        } else {                                                                                                 \
-            if (self_) { r.v[D] = sf_; r.tv[D] = tfx[D]; }                                                       \
-            else if ((r.rk[D] & 0xFF) != KP_INROW) r.tv[D] = fetch_test(D, r.rk[D]);                             \
-        }                                                                                                        \
+                // ---- register position: in-register splits + self-score compare, digit by digit.
+                //      reference: if s < (double)best: best = f32(s)   <=>   sf < best || (sf == best && sf > s) ----
+                uint32_t flag = 0;
+#define KP_FIN(D)                                                                                     \
+    if ((need >> (D)) & 1u) {                                                                         \
+        const float sf_ = sfx[D];                                                                     \
+        if (sf_ < v[D] || (sf_ == v[D] && ((rupm >> (D)) & 1u))) { v[D] = sf_; flag |= 1u << (D); }   \
     }
-#define KP_SP(D, A, B, J) Ops::template split<D, A, B, J>(r, rankbase);
+#define KP_SP(D, A, B) v[D] = fminf(v[D], __fadd_rn(v[A], v[B]));
                 if (R0 == 1) {
                     KP_FIN(0)
                 } else if (R0 == 3) {
                     KP_FIN(0) KP_FIN(1)
-                    KP_SP(2, 0, 1, 0) KP_FIN(2)
+                    KP_SP(2, 0, 1) KP_FIN(2)
                 } else if (R0 == 7) {
                     KP_FIN(0) KP_FIN(1) KP_FIN(2)
-                    KP_SP(3, 0, 1, 0) KP_FIN(3)
-                    KP_SP(4, 0, 2, 0) KP_FIN(4)
-                    KP_SP(5, 1, 2, 0) KP_FIN(5)
-                    KP_SP(6, 0, 5, 0) KP_SP(6, 1, 4, 1) KP_SP(6, 2, 3, 2) KP_FIN(6)
+                    KP_SP(3, 0, 1) KP_FIN(3)
+                    KP_SP(4, 0, 2) KP_FIN(4)
+                    KP_SP(5, 1, 2) KP_FIN(5)
+                    KP_SP(6, 0, 5) KP_SP(6, 1, 4) KP_SP(6, 2, 3) KP_FIN(6)
                 } else {
                     KP_FIN(0) KP_FIN(1) KP_FIN(2) KP_FIN(3)
-                    KP_SP(4, 0, 2, 0) KP_FIN(4)     // R = A|G
-                    KP_SP(5, 1, 3, 0) KP_FIN(5)     // Y = C|T
-                    KP_SP(6, 2, 1, 0) KP_FIN(6)     // S = G|C
-                    KP_SP(7, 0, 3, 0) KP_FIN(7)     // W = A|T
-                    KP_SP(8, 2, 3, 0) KP_FIN(8)     // K = G|T
-                    KP_SP(9, 0, 1, 0) KP_FIN(9)     // M = A|C
-                    KP_SP(10, 1, 8, 0) KP_SP(10, 2, 5, 1) KP_SP(10, 3, 6, 2) KP_FIN(10)   // B
-                    KP_SP(11, 0, 8, 0) KP_SP(11, 2, 7, 1) KP_SP(11, 3, 4, 2) KP_FIN(11)   // D
-                    KP_SP(12, 0, 5, 0) KP_SP(12, 1, 7, 1) KP_SP(12, 3, 9, 2) KP_FIN(12)   // H
-                    KP_SP(13, 0, 6, 0) KP_SP(13, 1, 4, 1) KP_SP(13, 2, 9, 2) KP_FIN(13)   // V
-                    KP_SP(14, 6, 7, 0) KP_SP(14, 8, 9, 1) KP_SP(14, 4, 5, 2) KP_SP(14, 0, 10, 3)
-                    KP_SP(14, 1, 11, 4) KP_SP(14, 2, 12, 5) KP_SP(14, 3, 13, 6) KP_FIN(14)  // N
+                    KP_SP(4, 0, 2) KP_FIN(4)     // R = A|G
+                    KP_SP(5, 1, 3) KP_FIN(5)     // Y = C|T
+                    KP_SP(6, 2, 1) KP_FIN(6)     // S = G|C
+                    KP_SP(7, 0, 3) KP_FIN(7)     // W = A|T
+                    KP_SP(8, 2, 3) KP_FIN(8)     // K = G|T
+                    KP_SP(9, 0, 1) KP_FIN(9)     // M = A|C
+                    KP_SP(10, 1, 8) KP_SP(10, 2, 5) KP_SP(10, 3, 6) KP_FIN(10)   // B
+                    KP_SP(11, 0, 8) KP_SP(11, 2, 7) KP_SP(11, 3, 4) KP_FIN(11)   // D
+                    KP_SP(12, 0, 5) KP_SP(12, 1, 7) KP_SP(12, 3, 9) KP_FIN(12)   // H
+                    KP_SP(13, 0, 6) KP_SP(13, 1, 4) KP_SP(13, 2, 9) KP_FIN(13)   // V
+                    KP_SP(14, 6, 7) KP_SP(14, 8, 9) KP_SP(14, 4, 5) KP_SP(14, 0, 10)
+                    KP_SP(14, 1, 11) KP_SP(14, 2, 12) KP_SP(14, 3, 13) KP_FIN(14)  // N
                 }
 #undef KP_FIN
 #undef KP_SP
                 // ---- store the row ----
 #pragma unroll
-                for (int c = R0; c < NG * 4; c++) { r.v[c] = 0.f; if (CV) r.tv[c] = 0.f; }
+                for (int c = R0; c < NG * 4; c++) v[c] = 0.f;
 #pragma unroll
                 for (int g = 0; g < NG; g++) {
-                    float4 o = make_float4(r.v[4 * g], r.v[4 * g + 1], r.v[4 * g + 2], r.v[4 * g + 3]);
+                    float4 o = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
                     S[g * rp + srow] = o;
                     __stcs(otile + g * rp + srow, o);  // next read is a whole wave away: do not keep it in L2
-                    if (CV) {
-                        float4 ot = make_float4(r.tv[4 * g], r.tv[4 * g + 1], r.tv[4 * g + 2], r.tv[4 * g + 3]);
-                        ((float4 *)(p.test + (size_t)tile * stride))[g * rp + srow] = ot;
-                    }
                 }
-                if (!CV) p.flags[(size_t)tile * rp + srow] = (uint16_t)r.flag;
+                p.flags[(size_t)tile * rp + srow] = (uint16_t)flag;
             }
-            __syncwarp();  // rows of this round (shared S, and for CV the global test rows) visible to the warp
+            __syncwarp();  // rows of this round visible to the warp
         }
     }
-#undef KP_HS_LOAD
-#undef KP_HS_USE
-#undef KP_HS_STREAM
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CV job helpers.  A CV job is the DP above on the TRAIN counts (total - held-out); the held-out loss of
+// the optimal partition is then summed along the partition tree (_CV.py:46-51, :71-78): a leaf contributes
+// the float32 held-out loss of the unsplit pattern, an inner node the float32 sum of its two children.
+// ---------------------------------------------------------------------------------------------------
+__global__ void kp_train_counts_kernel(const long long *tot, const long long *held, long long *train, unsigned long long n)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        train[i] = tot[i] - held[i];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -679,6 +541,65 @@ __device__ __forceinline__ float kp_best_at(const KpTables &tb, const uint16_t *
     return best[L.tile * tb.tile_stride + ((size_t)(L.d0 >> 2) * tb.rp + L.srow) * 4 + (L.d0 & 3)];
 }
 
+// counts of one pattern from an expanded table: sum over the base rows of its row and the bases of its digit
+__device__ __forceinline__ void kp_counts_from_expanded(const KpTables &tb, const uint8_t *rowtab, const long long *eM,
+                                                        const long long *eU, unsigned long long tile, uint32_t srow,
+                                                        uint32_t d0, unsigned long long &M, unsigned long long &U)
+{
+    const uint16_t *bs_off = (const uint16_t *)(rowtab + tb.rt_bs_off);
+    const uint16_t *bs = (const uint16_t *)(rowtab + tb.rt_bs);
+    const uint32_t nb = (uint32_t)tb.nb0;
+    const unsigned bm = tb.r0 == 15 ? kpc_bm15[d0] : (tb.r0 == 7 ? kpc_bm7[d0] : (tb.r0 == 3 ? kpc_bm3[d0] : kpc_bm1[d0]));
+    M = 0; U = 0;
+    for (int i = bs_off[srow]; i < bs_off[srow + 1]; i++)
+        for (uint32_t b = 0; b < nb; b++)
+            if ((bm >> b) & 1u) {
+                size_t g = (size_t)tile * tb.tile_kmers + (size_t)bs[i] * nb + b;
+                M += (unsigned long long)eM[g];
+                U += (unsigned long long)eU[g];
+            }
+}
+
+// held-out loss of every leaf of a backtracked partition: RN_f32 of _CV.py:73-78 (level >= 1) or :15-20 (k-mers)
+__global__ void kp_cv_leaf_kernel(const KpTables *tab, const uint8_t *rowtab, const long long *eMtr, const long long *eUtr,
+                                  const long long *eMte, const long long *eUte, double alpha, double beta, double penalty,
+                                  const unsigned long long *pats, const unsigned long long *counts, unsigned long long cap,
+                                  float *out)
+{
+    const KpTables &tb = *tab;
+    const uint16_t *srow_of_row = (const uint16_t *)(rowtab + tb.rt_srow_of_row);
+    const uint8_t *row_level = rowtab + tb.rt_row_level;
+    __shared__ double2 logtab[128];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) logtab[i] = make_double2(kpc_logTab[2 * i], kpc_logTab[2 * i + 1]);
+    __syncthreads();
+    unsigned long long n = counts[0] < cap ? counts[0] : cap;
+    const KpLogK K = kp_logk_load();
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        KpLoc L = kp_locate_dev(tb, srow_of_row, pats[i]);
+        unsigned long long Mtr, Utr, Mte, Ute;
+        kp_counts_from_expanded(tb, rowtab, eMtr, eUtr, L.tile, L.srow, L.d0, Mtr, Utr);
+        kp_counts_from_expanded(tb, rowtab, eMte, eUte, L.tile, L.srow, L.d0, Mte, Ute);
+        bool kmer = row_level[L.srow] == 0 && L.d0 < (uint32_t)tb.nb0;
+        unsigned long long x = L.tile;
+        for (int h = 0; h < tb.nhigh; h++) {
+            int e = tb.highpos[h];
+            if (x % tb.radix[e] >= tb.nbase[e]) kmer = false;
+            x /= tb.radix[e];
+        }
+        double t;
+        if (kmer) {
+            double s;
+            kp_leaf_cv(Mtr, Utr, Mte, Ute, alpha, beta, penalty, logtab, s, t);
+        } else {
+            double lp, l1;
+            kp_self_score_t<unsigned long long>(Mtr, Utr, alpha, beta, penalty, logtab, K, lp, l1);
+            t = kp_test_ll_t<unsigned long long>(Mte, Ute, lp, l1);
+        }
+        out[i] = __double2float_rn(t);
+    }
+}
+
 // The split the reference would have recorded for `pat` (w_numba.py:36-49, :62-64): 0xFF if the pattern is
 // kept whole, else position*8 + j of the first split in scan order whose float32 child sum is the minimum.
 __device__ uint8_t kp_split_code_dev(const KpTables &tb, const uint16_t *srow_of_row, const float *best,
@@ -791,7 +712,7 @@ __global__ void kp_backtrack_init_kernel(KpBtNode *fa, unsigned long long top, u
 
 // rank sort by key (keys are distinct): out[rank] = pat
 __global__ void kp_backtrack_sort_kernel(const KpBtNode *leaves, const unsigned long long *counts,
-                                         unsigned long long cap, unsigned long long *out)
+                                         unsigned long long cap, unsigned long long *out, unsigned long long *keys_out)
 {
     unsigned long long n = counts[0];
     if (n > cap) n = cap;
@@ -807,7 +728,7 @@ __global__ void kp_backtrack_sort_kernel(const KpBtNode *leaves, const unsigned 
             for (unsigned long long t = 0; t < lim; t++) rank += keys[t] < mykey;
             __syncthreads();
         }
-        if (i < n) out[rank] = leaves[i].pat;
+        if (i < n) { out[rank] = leaves[i].pat; keys_out[rank] = mykey; }
     }
 }
 

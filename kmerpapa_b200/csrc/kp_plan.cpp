@@ -277,13 +277,12 @@ int kp_build_host_plan(const char *gen_pat, KpHostPlan &P, std::string &err)
     }
     t.maxhs = (uint32_t)((7 * t.nhigh + 3) & ~3);
     if (t.maxhs < 4) t.maxhs = 4;
-    for (int cv = 0; cv < 2; cv++)
-        for (int wide = 0; wide < 2; wide++) {
-            size_t b = (size_t)t.ng * t.rp * 16;                       // S rows
-            b += (size_t)tk * (cv ? 4 : 2) * (wide ? 8 : 4);            // base counts of the tile
-            b += (size_t)t.maxhs * 9 + 16;                              // high split list (two tiles, rank) + count
-            t.warp_smem_bytes[cv][wide] = (uint32_t)((b + 15) & ~(size_t)15);
-        }
+    for (int wide = 0; wide < 2; wide++) {
+        size_t b = (size_t)t.ng * t.rp * 16;          // the warp's copy of its tile
+        b += (size_t)tk * 2 * (wide ? 8 : 4);          // base counts of the tile
+        b += (size_t)t.maxhs * 8 + 16;                 // high split list (two child tiles each) + count
+        t.warp_smem_bytes[wide] = (uint32_t)((b + 15) & ~(size_t)15);
+    }
 
     // ---- tiles sorted by high level ----
     int nhl = 1;

@@ -63,5 +63,5 @@ struct KpTables {
     uint32_t rt_bs;           // u16 [...]           base-row index (low k-mer index / nb0)
     uint32_t rt_srow_of_row;  // u16 [nrows]         natural row -> srow
     uint32_t maxhs;                  // capacity of a tile's high-split list (7 per high position, rounded to 4)
-    uint32_t warp_smem_bytes[2][2];  // per-warp shared memory of the DP kernel [cv][wide]
+    uint32_t warp_smem_bytes[2];     // per-warp shared memory of the DP kernel [wide]
 };

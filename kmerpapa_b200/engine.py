@@ -122,15 +122,18 @@ class PartitionPlan:
         return np.float32(table[self.top_elem].item())
 
     # -- K5: backtrack ---------------------------------------------------------------------------
-    def backtrack(self, best, kept, cap=65536):
-        """Dense pattern numbers of the optimal partition in the reference's emission order."""
+    TOP = (1 << 64) - 1
+
+    def backtrack(self, best, kept, cap=65536, root=None):
+        """Dense pattern numbers of the optimal partition of `root` (default: the general pattern) in the
+        reference's emission order."""
         torch = _torch()
         while True:
             ws = self._buffer("btws", int(self.lib.kp_backtrack_ws_bytes(cap)), torch.uint8)
             out = np.empty(cap, dtype=np.uint64)
             n = ctypes.c_uint64(0)
-            rc = self.lib.kp_backtrack(self.handle, best.data_ptr(), kept.data_ptr(), ws.data_ptr(), cap, out.ctypes.data,
-                                       ctypes.byref(n), self._stream())
+            rc = self.lib.kp_backtrack(self.handle, best.data_ptr(), kept.data_ptr(), ws.data_ptr(), cap,
+                                       self.TOP if root is None else int(root), out.ctypes.data, ctypes.byref(n), self._stream())
             if rc == 0:
                 return out[: n.value].copy()
             msg = self.lib.kp_last_error().decode()
@@ -148,21 +151,46 @@ class PartitionPlan:
         return out
 
     # -- CV job ----------------------------------------------------------------------------------
-    def cv_job(self, eMtot, eUtot, eMte, eUte, max_count, alpha, beta, penalty, read_top=True):
-        """One fold x alpha x penalty.  Returns (np.float32 train, np.float32 test) of the general pattern,
-        or the (train, test) device tables when read_top is False."""
+    def cv_job(self, eMtot, eUtot, eMte, eUte, max_count, alpha, beta, penalty, read_top=True, cap=65536):
+        """One fold x alpha x penalty: the DP on the train counts (total - held-out).  Returns
+        (np.float32 train, np.float32 held-out) loss of the general pattern; with read_top=False only the
+        DP runs and the device tables (train, kept) are returned."""
         torch = _torch()
         n = int(self.info.table_elems)
+        ne = int(self.info.expanded_elems)
         train = self._buffer("cvtrain", n, torch.float32)
-        test = self._buffer("cvtest", n, torch.float32)
+        kept = self._buffer("cvkept", int(self.info.kept_elems), torch.int16)
+        eMtr = self._buffer("cv_expMtr", ne, torch.int64)
+        eUtr = self._buffer("cv_expUtr", ne, torch.int64)
         top = (ctypes.c_float * 2)()
-        check(self.lib.kp_dp_cv_job(self.handle, eMtot.data_ptr(), eUtot.data_ptr(), eMte.data_ptr(), eUte.data_ptr(),
-                                    int(max_count), float(alpha), float(beta), float(penalty), train.data_ptr(),
-                                    test.data_ptr(), ctypes.cast(top, ctypes.c_void_p) if read_top else None,
-                                    self._stream()), "kp_dp_cv_job")
+        while True:
+            ws = self._buffer("btws", int(self.lib.kp_backtrack_ws_bytes(cap)), torch.uint8)
+            rc = self.lib.kp_dp_cv_job(self.handle, eMtot.data_ptr(), eUtot.data_ptr(), eMte.data_ptr(), eUte.data_ptr(),
+                                       int(max_count), float(alpha), float(beta), float(penalty), eMtr.data_ptr(),
+                                       eUtr.data_ptr(), train.data_ptr(), kept.data_ptr(), ws.data_ptr(), cap,
+                                       ctypes.cast(top, ctypes.c_void_p) if read_top else None, self._stream())
+            if rc == 0:
+                break
+            msg = self.lib.kp_last_error().decode()
+            if "capacity" in msg and cap < (1 << 26):
+                cap *= 8
+                continue
+            raise KpError("kp_dp_cv_job: " + msg)
+        self._cv_state = (eMtr, eUtr, eMte, eUte, float(alpha), float(beta), float(penalty))
         if not read_top:
-            return train, test
+            return train, kept
         return np.float32(top[0]), np.float32(top[1])
+
+    def cv_heldout(self, root, cap=65536):
+        """Held-out loss of the best partition of pattern `root` for the last cv_job (reference: test_score_mem[root])."""
+        torch = _torch()
+        eMtr, eUtr, eMte, eUte, alpha, beta, penalty = self._cv_state
+        ws = self._buffer("btws", int(self.lib.kp_backtrack_ws_bytes(cap)), torch.uint8)
+        out = ctypes.c_float(0)
+        check(self.lib.kp_cv_heldout(self.handle, self._buf["cvtrain"].data_ptr(), self._buf["cvkept"].data_ptr(),
+                                     eMtr.data_ptr(), eUtr.data_ptr(), eMte.data_ptr(), eUte.data_ptr(), alpha, beta, penalty,
+                                     int(root), ws.data_ptr(), cap, ctypes.byref(out), self._stream()), "kp_cv_heldout")
+        return np.float32(out.value)
 
     # -- output stage ----------------------------------------------------------------------------
     def pattern_counts(self, kM, kU, patnums):

@@ -139,17 +139,20 @@ def test_cv_jobs_against_reference_tables(eng, oracle, path):
             for f in range(nf):
                 kMf, kUf = plan.upload_kmer_tables(Mf[:, f], Uf[:, f], name="t_fold")
                 fold = plan.expand(kMf, kUf, name="t_fold_e")
+                ref_tr = g["train_tables"][gi][:, f]
+                if gi == len(alphas) * len(pens) - 1:
+                    ref_te = g["last_test_table"][:, f]
+                else:
+                    _, ref_te = oracle.cv_job(gp, Mtot, Utot, Mf[:, f], Uf[:, f], alpha, betas[f], pen)
                 for wide_mc in (mc, 1 << 40):
-                    train, test = plan.cv_job(tot[0], tot[1], fold[0], fold[1], wide_mc, alpha, betas[f], pen, read_top=False)
-                    tr, te = plan.gather(train), plan.gather(test)
-                    assert np.array_equal(_bits(tr), _bits(g["train_tables"][gi][:, f]))
-                    if gi == len(alphas) * len(pens) - 1:
-                        assert np.array_equal(_bits(te), _bits(g["last_test_table"][:, f]))
-                    else:
-                        _, ote = oracle.cv_job(gp, Mtot, Utot, Mf[:, f], Uf[:, f], alpha, betas[f], pen)
-                        assert np.array_equal(_bits(te), _bits(ote))
                     top = plan.cv_job(tot[0], tot[1], fold[0], fold[1], wide_mc, alpha, betas[f], pen)
-                    assert top[0].tobytes() == tr[-1].tobytes() and top[1].tobytes() == te[-1].tobytes()
+                    # train table: every cell; held-out loss: the general pattern (all the reference reads) ...
+                    assert np.array_equal(_bits(plan.gather(plan._buf["cvtrain"])), _bits(ref_tr))
+                    assert top[0].tobytes() == ref_tr[-1].tobytes() and top[1].tobytes() == ref_te[-1].tobytes()
+                # ... and a spread of other patterns, against the reference's whole test table
+                rng = np.random.default_rng(gi * 31 + f)
+                for root in rng.choice(plan.npat, size=min(40, plan.npat), replace=False):
+                    assert plan.cv_heldout(int(root)).tobytes() == ref_te[root].tobytes()
             gi += 1
 
 
@@ -196,9 +199,12 @@ def test_random_cv_job_against_oracle(eng, oracle, gen_pat, seed):
     fold = plan.expand(kMf, kUf, name="r_fold_e")
     otr, ote = oracle.cv_job(gen_pat, M, U, Mte, Ute, alpha, beta, pen)
     for mc in (int(M.sum() + U.sum()), 1 << 40):
-        train, test = plan.cv_job(tot[0], tot[1], fold[0], fold[1], mc, alpha, beta, pen, read_top=False)
-        assert np.array_equal(_bits(plan.gather(train)), _bits(otr))
-        assert np.array_equal(_bits(plan.gather(test)), _bits(ote))
+        top = plan.cv_job(tot[0], tot[1], fold[0], fold[1], mc, alpha, beta, pen)
+        assert np.array_equal(_bits(plan.gather(plan._buf["cvtrain"])), _bits(otr))
+        assert top[0].tobytes() == otr[-1].tobytes() and top[1].tobytes() == ote[-1].tobytes()
+    rng2 = np.random.default_rng(seed + 100)
+    for root in rng2.choice(plan.npat, size=min(60, plan.npat), replace=False):
+        assert plan.cv_heldout(int(root)).tobytes() == ote[root].tobytes()
 
 
 def test_7mer_test_data_final_dp(eng, oracle):

@@ -31,7 +31,7 @@ for rep in range(reps):
     else:
         kMf, kUf = plan.upload_kmer_tables(pos // 5, neg // 5, name="pf")
         fM, fU = plan.expand(kMf, kUf, name="pfe")
-        plan.cv_job(eM, eU, fM, fU, mc, 1.0, beta, 6.0, read_top=False)
+        print(plan.cv_job(eM, eU, fM, fU, mc, 1.0, beta, 6.0))
     e1.record()
     torch.cuda.synchronize()
     print(f"{kind} {gen_pat} rep {rep}: {e0.elapsed_time(e1):.3f} ms, {plan.npat / e0.elapsed_time(e1) / 1e6:.2f} Gpat/s", flush=True)
