@@ -1,6 +1,7 @@
 // kp_api.cu — C ABI of libkpapa.so (see include/kmerpapa_b200.h for the contract).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -311,6 +312,8 @@ int kp_dp_single(kp_plan *p, const int64_t *d_expM, const int64_t *d_expU, uint6
     prm.alpha = alpha; prm.beta = beta; prm.penalty = penalty;
     prm.best = d_best;
     prm.flags = d_kept;
+    prm.pf_dist = KP_PF_DIST;
+    if (const char *e = getenv("KP_PF_DIST")) prm.pf_dist = atoi(e);   // tuning knob
     return launch_dp(p, wide, prm, (cudaStream_t)stream);
 }
 

@@ -37,6 +37,9 @@
 #include "kp_tables.h"
 
 #define KP_MAX_WARPS 14      // tiles in flight per SM (<= 128 registers per thread)
+#ifndef KP_PF_DIST
+#define KP_PF_DIST 4         // L2 prefetch distance of the child-tile stream, in (32 rows x 1 split) steps
+#endif
 
 template <bool WIDE> struct KpCnt { typedef unsigned int type; };
 template <> struct KpCnt<true> { typedef unsigned long long type; };
@@ -144,6 +147,7 @@ struct KpDpParams {
     uint32_t ntiles_wave;
     uint32_t *counter;          // next unclaimed entry of tile_list (zeroed before the launch)
     int leaf_wave;              // wave 0: rows of level 0 hold k-mers at the single-nucleotide digits
+    int pf_dist;                // L2 prefetch distance of the child-tile stream, in (32 rows x 1 split) steps
     const long long *e0, *e1;   // expanded counts M, U  [ntiles][tile_kmers]
     double alpha, beta, penalty;
     float *best;                // best loss per pattern
@@ -246,8 +250,23 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
             float4 xa0[NG], xb0[NG], xa1[NG], xb1[NG];
             int ls = 0, lrow = lane;          // split and row of the next load
             int us = 0, urow = lane;          // split and row of the next use
+            int ps = 0, prow = lane;          // split and row of the next L2 prefetch (KP_PF_DIST steps ahead)
+            // register-free deepening of the pipeline: every step also asks L2 for the lines of a later step
+#define KP_FL_PREFETCH()                                                                              \
+    if (prow < nrows) {                                                                               \
+        if ((lane & 3) == 0) {                                                                        \
+            const float4 *a_ = (const float4 *)(tbase + (size_t)hs1[ps] * stride) + prow;             \
+            const float4 *b_ = (const float4 *)(tbase + (size_t)hs2[ps] * stride) + prow;             \
+            _Pragma("unroll") for (int g = 0; g < NG; g++) {                                          \
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a_ + g * rp));                          \
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(b_ + g * rp));                          \
+            }                                                                                         \
+        }                                                                                             \
+        if (++ps == nhs) { ps = 0; prow += 32; }                                                      \
+    }
 #define KP_FL_LOAD(xa, xb)                                                                            \
     {                                                                                                 \
+        KP_FL_PREFETCH()                                                                              \
         const int row_ = lrow < nrows ? lrow : nrows - 1;   /* idle lanes of the last chunk re-read a valid row */ \
         const float4 *a_ = (const float4 *)(tbase + (size_t)hs1[ls] * stride) + row_;                 \
         const float4 *b_ = (const float4 *)(tbase + (size_t)hs2[ls] * stride) + row_;                 \
@@ -271,7 +290,10 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
             us = 0; urow += 32;                                                                       \
         }                                                                                             \
     }
-            if (nstep > 0) KP_FL_LOAD(xa0, xb0)
+            if (nstep > 0) {
+                for (int i = 0; i < p.pf_dist; i++) KP_FL_PREFETCH()
+                KP_FL_LOAD(xa0, xb0)
+            }
             int t = 0;
             for (; t + 2 <= nstep; t += 2) {
                 KP_FL_LOAD(xa1, xb1)
@@ -282,6 +304,7 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
             if (t < nstep) KP_FL_USE(xa0, xb0)
 #undef KP_FL_LOAD
 #undef KP_FL_USE
+#undef KP_FL_PREFETCH
             if (nstep == 0)  // no high-position split (wave 0, or a pattern without high positions)
                 for (int srow = lane; srow < nrows; srow += 32) {
 #pragma unroll
