@@ -38,7 +38,7 @@
 
 #define KP_MAX_WARPS 14      // tiles in flight per SM (<= 128 registers per thread)
 #ifndef KP_PF_DIST
-#define KP_PF_DIST 4         // L2 prefetch distance of the child-tile stream, in (32 rows x 1 split) steps
+#define KP_PF_DIST 2         // L2 prefetch distance of the child-tile stream, in (32 rows x 1 split) steps
 #endif
 
 template <bool WIDE> struct KpCnt { typedef unsigned int type; };
