@@ -273,7 +273,7 @@ def bench_single(args, rank, world, local):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "cfg3 synthetic 9-mer (neg-binomial), single penalty+pseudo, full DP + backtrack",
                    "gen_pat": GEN_PAT, "npat": npat, "alpha": ALPHA, "penalty": PENALTY, "partition_patterns": int(len(patnums)),
-                   "loss": float(loss), "l2": "score+split tables 12.9 GB >> 126 MB L2, no flush needed",
+                   "loss": float(loss), "l2": "score table 11 GB >> 126 MB L2, no flush needed",
                    "replicas": world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": load_traffic("single_dp_bytes"), "kernel": "kp_dp_rows_kernel (fused lazy score + min-plus), all 16 wave launches of one DP",
@@ -366,7 +366,7 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "cfg4 synthetic 9-mer, 3x3 penalty x pseudo grid, 5-fold CV sharded by job",
                        "gen_pat": GEN_PAT, "jobs": cvres["jobs"], "alphas": CV_ALPHAS, "penalties": CV_PENALTIES,
-                       "nfolds": CV_FOLDS, "l2": "train/test table 20.6 GB per job >> 126 MB L2, no flush needed"},
+                       "nfolds": CV_FOLDS, "l2": "train table 11 GB per job >> 126 MB L2, no flush needed"},
             "roofline": {"bound": "hbm", "achieved": cvres["achieved_gbs_per_gpu"], "peak": cvres["peak"], "unit": "GB/s",
                          "frac": cvres["frac_per_gpu"], "traffic": load_traffic("cv_job_bytes"),
                          "kernel": "kp_dp_rows_kernel on train counts + backtrack/leaf kernels, per GPU", "algorithmic_bytes_per_pattern": ALGO_BYTES_CV,
@@ -376,7 +376,7 @@ def main():
                     "note": "each step packs the host fold tables (H2D) and reads every job's losses back (D2H)"},
             "cv_grid": cvres, "gpu_launches": cvres["launches"], "clocks": cvres["clocks"],
         }
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_sample_run()
         line["cpu_baseline"] = {
             "value": r["npat"] / r["seconds"], "unit": "patterns/s", "cores": r["threads"], "kind": "port",
