@@ -91,10 +91,36 @@ def _pattern_counts(gen_pat, contextD, names):
     return [(int(m), int(u)) for m, u in zip(M, U)]
 
 
+def _init_distributed():
+    """Under torchrun (WORLD_SIZE > 1) every process takes one GPU and joins an NCCL group: the CV grid is then
+    sharded by job across the GPUs.  Returns this process's rank."""
+    import os
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist.get_rank()
+
+
 def main(args=None):
     """Runs the program; returns the exit code (0 also on input errors, like the reference)."""
     parser = get_parser()
     args = parser.parse_args(args=args)
+    rank = _init_distributed()
+    if rank != 0:   # only rank 0 reports and writes files; the others just run their share of the CV jobs
+        import os
+
+        args.verbosity = 0
+        args.output = open(os.devnull, "w")
+        if args.CVfile is not None:
+            args.CVfile = open(os.devnull, "w")
     if args.version:
         print("version:", __version__)
         print()
