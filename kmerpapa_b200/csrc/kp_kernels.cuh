@@ -126,15 +126,28 @@ template <int R0> __device__ __forceinline__ unsigned kp_bm(int d)
     return R0 == 15 ? kpc_bm15[d] : (R0 == 7 ? kpc_bm7[d] : (R0 == 3 ? kpc_bm3[d] : kpc_bm1[d]));
 }
 
-// Float32 estimate of the self-score (w_numba.py:56-61) for the score filter.  Relative error < 1e-5
-// (fast log: < 2^-21 absolute; log(1-p) by its series below p = 2^-5; no cancellation: both terms are >= 0);
-// the filter uses a margin of 2e-4 |s| + 0.01.  A NaN estimate (p == 0, ...) never skips the exact score.
-__device__ __forceinline__ float kp_score_estimate(float Mf, float Uf, float alpha, float ab, float penalty)
+// Float32 lower bound of the self-score (w_numba.py:56-61) for the score filter, two patterns at a time with
+// the packed f32x2 instructions of sm_100 (FADD2/FMUL2/FFMA2).  The estimate's relative error is < 1e-5 (fast
+// log: < 2^-21 absolute; log(1-p) by its series below p = 2^-5; no cancellation: both terms are >= 0); the bound
+// subtracts a margin of 2e-4 |s| + 0.01.  A NaN (p == 0, ...) never skips the exact score.
+__device__ __forceinline__ float2 kp_score_lower_bound2(float2 Mf, float2 Uf, float alpha, float ab, float penalty)
 {
-    float p = __fdividef(Mf + alpha, (Mf + Uf) + ab);
-    float lp = __logf(p);
-    float l1 = p < 0.03125f ? -p * (1.0f + p * (0.5f + p * (0.33333334f + 0.25f * p))) : __logf(1.0f - p);
-    return penalty - 2.0f * (Mf * lp + Uf * l1);
+    const float2 num = __fadd2_rn(Mf, make_float2(alpha, alpha));
+    const float2 den = __fadd2_rn(__fadd2_rn(Mf, Uf), make_float2(ab, ab));
+    const float2 p = make_float2(__fdividef(num.x, den.x), __fdividef(num.y, den.y));
+    const float2 lp = make_float2(__logf(p.x), __logf(p.y));
+    // log(1-p) = -p (1 + p (1/2 + p (1/3 + p/4)))  for p < 2^-5
+    float2 t = __ffma2_rn(p, make_float2(0.25f, 0.25f), make_float2(0.33333334f, 0.33333334f));
+    t = __ffma2_rn(p, t, make_float2(0.5f, 0.5f));
+    t = __ffma2_rn(p, t, make_float2(1.0f, 1.0f));
+    float2 l1 = __fmul2_rn(make_float2(-p.x, -p.y), t);
+    if (!(p.x < 0.03125f)) l1.x = __logf(1.0f - p.x);
+    if (!(p.y < 0.03125f)) l1.y = __logf(1.0f - p.y);
+    const float2 ll = __ffma2_rn(Mf, lp, __fmul2_rn(Uf, l1));                       // M log p + U log(1-p)  (<= 0)
+    const float2 est = __ffma2_rn(ll, make_float2(-2.0f, -2.0f), make_float2(penalty, penalty));
+    // est - (2e-4 |est| + 0.01)
+    const float2 mar = __ffma2_rn(make_float2(fabsf(est.x), fabsf(est.y)), make_float2(2e-4f, 2e-4f), make_float2(0.01f, 0.01f));
+    return __fadd2_rn(est, make_float2(-mar.x, -mar.y));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -275,11 +288,13 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
     }
 #define KP_FL_USE(xa, xb)                                                                             \
     {                                                                                                 \
-        _Pragma("unroll") for (int g = 0; g < NG; g++) {                                              \
-            v[4 * g + 0] = fminf(v[4 * g + 0], __fadd_rn(xa[g].x, xb[g].x));                          \
-            v[4 * g + 1] = fminf(v[4 * g + 1], __fadd_rn(xa[g].y, xb[g].y));                          \
-            v[4 * g + 2] = fminf(v[4 * g + 2], __fadd_rn(xa[g].z, xb[g].z));                          \
-            v[4 * g + 3] = fminf(v[4 * g + 3], __fadd_rn(xa[g].w, xb[g].w));                          \
+        _Pragma("unroll") for (int g = 0; g < NG; g++) {   /* packed f32x2 adds (FADD2), IEEE round-to-nearest */ \
+            const float2 lo_ = __fadd2_rn(make_float2(xa[g].x, xa[g].y), make_float2(xb[g].x, xb[g].y)); \
+            const float2 hi_ = __fadd2_rn(make_float2(xa[g].z, xa[g].w), make_float2(xb[g].z, xb[g].w)); \
+            v[4 * g + 0] = fminf(v[4 * g + 0], lo_.x);                                                \
+            v[4 * g + 1] = fminf(v[4 * g + 1], lo_.y);                                                \
+            v[4 * g + 2] = fminf(v[4 * g + 2], hi_.x);                                                \
+            v[4 * g + 3] = fminf(v[4 * g + 3], hi_.y);                                                \
         }                                                                                             \
         if (++us == nhs) {   /* chunk complete: park its minima, start the next chunk */              \
             if (urow < nrows) {                                                                       \
@@ -330,10 +345,12 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
 #pragma unroll
                     for (int g = 0; g < NG; g++) {
                         float4 xa = a[g * rp], xb = b[g * rp];
-                        v[4 * g + 0] = fminf(v[4 * g + 0], __fadd_rn(xa.x, xb.x));
-                        v[4 * g + 1] = fminf(v[4 * g + 1], __fadd_rn(xa.y, xb.y));
-                        v[4 * g + 2] = fminf(v[4 * g + 2], __fadd_rn(xa.z, xb.z));
-                        v[4 * g + 3] = fminf(v[4 * g + 3], __fadd_rn(xa.w, xb.w));
+                        const float2 lo_ = __fadd2_rn(make_float2(xa.x, xa.y), make_float2(xb.x, xb.y));
+                        const float2 hi_ = __fadd2_rn(make_float2(xa.z, xa.w), make_float2(xb.z, xb.w));
+                        v[4 * g + 0] = fminf(v[4 * g + 0], lo_.x);
+                        v[4 * g + 1] = fminf(v[4 * g + 1], lo_.y);
+                        v[4 * g + 2] = fminf(v[4 * g + 2], hi_.x);
+                        v[4 * g + 3] = fminf(v[4 * g + 3], hi_.y);
                     }
                 }
                 // ---- counts of this row at the single-nucleotide digits of the register position ----
@@ -353,14 +370,16 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
 #pragma unroll
                     for (int b = 0; b < NB; b++) { mf[b] = (float)m[b]; uf[b] = (float)u[b]; }
 #pragma unroll
-                    for (int d = 0; d < R0; d++) {
-                        float Mf = 0.f, Uf = 0.f;
+                    for (int h = 0; h < (R0 + 1) / 2; h++) {   // two digits per evaluation
+                        float2 Mf = make_float2(0.f, 0.f), Uf = make_float2(0.f, 0.f);
 #pragma unroll
-                        for (int b = 0; b < NB; b++)
-                            if ((kp_bm_c<R0>(d) >> b) & 1) { Mf += mf[b]; Uf += uf[b]; }
-                        float est = kp_score_estimate(Mf, Uf, alpha_f, ab_f, penalty_f);
-                        float margin = 2e-4f * fabsf(est) + 0.01f;
-                        if (!(est - margin > v[d])) need |= 1u << d;
+                        for (int b = 0; b < NB; b++) {
+                            if ((kp_bm_c<R0>(2 * h) >> b) & 1) { Mf.x += mf[b]; Uf.x += uf[b]; }
+                            if (2 * h + 1 < R0 && ((kp_bm_c<R0>(2 * h + 1) >> b) & 1)) { Mf.y += mf[b]; Uf.y += uf[b]; }
+                        }
+                        const float2 lb = kp_score_lower_bound2(Mf, Uf, alpha_f, ab_f, penalty_f);
+                        if (!(lb.x > v[2 * h])) need |= 1u << (2 * h);
+                        if (2 * h + 1 < R0 && !(lb.y > v[2 * h + 1])) need |= 1u << (2 * h + 1);
                     }
                     if (leafrow) need |= (1u << NB) - 1u;
                 }
