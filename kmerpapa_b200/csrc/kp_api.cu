@@ -48,22 +48,26 @@ struct kp_plan {
     size_t smem_optin = 0;
 };
 
+// the all-N tile shape (register radix 15, two N row positions: 225 rows) gets its row pitch at compile time
+#define KP_RP_NN 232
+
 template <bool WIDE>
-static const void *dp_kernel_for_radix(int r0)
+static const void *dp_kernel_for_radix(int r0, int rp)
 {
     switch (r0) {
-    case 1: return (const void *)kp_dp_rows_kernel<1, WIDE>;
-    case 3: return (const void *)kp_dp_rows_kernel<3, WIDE>;
-    case 7: return (const void *)kp_dp_rows_kernel<7, WIDE>;
-    default: return (const void *)kp_dp_rows_kernel<15, WIDE>;
+    case 1: return (const void *)kp_dp_rows_kernel<1, WIDE, 0>;
+    case 3: return (const void *)kp_dp_rows_kernel<3, WIDE, 0>;
+    case 7: return (const void *)kp_dp_rows_kernel<7, WIDE, 0>;
+    default:
+        return rp == KP_RP_NN ? (const void *)kp_dp_rows_kernel<15, WIDE, KP_RP_NN> : (const void *)kp_dp_rows_kernel<15, WIDE, 0>;
     }
 }
 
-template <int R0>
+template <int R0, int RP>
 static void launch_dp_r0(bool wide, int grid, int threads, size_t smem, cudaStream_t st, const KpDpParams &prm)
 {
-    if (wide) kp_dp_rows_kernel<R0, true><<<grid, threads, smem, st>>>(prm);
-    else kp_dp_rows_kernel<R0, false><<<grid, threads, smem, st>>>(prm);
+    if (wide) kp_dp_rows_kernel<R0, true, RP><<<grid, threads, smem, st>>>(prm);
+    else kp_dp_rows_kernel<R0, false, RP><<<grid, threads, smem, st>>>(prm);
 }
 
 // float32 sum of the leaves' held-out losses in the order of the partition tree (keys sorted ascending;
@@ -88,7 +92,10 @@ extern "C" {
 const char *kp_last_error(void) { return g_err.c_str(); }
 int kp_version(void) { return 100; }
 
-static const void *dp_kernel_ptr(int r0, bool wide) { return wide ? dp_kernel_for_radix<true>(r0) : dp_kernel_for_radix<false>(r0); }
+static const void *dp_kernel_ptr(int r0, int rp, bool wide)
+{
+    return wide ? dp_kernel_for_radix<true>(r0, rp) : dp_kernel_for_radix<false>(r0, rp);
+}
 
 int kp_plan_create(const char *gen_pat, int device, kp_plan **out)
 {
@@ -125,7 +132,7 @@ int kp_plan_create(const char *gen_pat, int device, kp_plan **out)
         if (nw > KP_MAX_WARPS) nw = KP_MAX_WARPS;
         p->nwarps[wide] = nw;
         // the attribute is per function, not per plan: always raise it to the device maximum
-        KP_CUDA(cudaFuncSetAttribute(dp_kernel_ptr(t.r0, wide), cudaFuncAttributeMaxDynamicSharedMemorySize,
+        KP_CUDA(cudaFuncSetAttribute(dp_kernel_ptr(t.r0, t.rp, wide), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)prop.sharedMemPerBlockOptin));
     }
     *out = p;
@@ -286,10 +293,13 @@ static int launch_dp(kp_plan *p, bool wide, KpDpParams prm, cudaStream_t st)
         if (grid > (uint64_t)p->sm_count) grid = p->sm_count;
         size_t sm = 2048 + t.rt_bytes + (size_t)warps * t.warp_smem_bytes[wide];
         switch (t.r0) {
-        case 1: launch_dp_r0<1>(wide, (int)grid, warps * 32, sm, st, prm); break;
-        case 3: launch_dp_r0<3>(wide, (int)grid, warps * 32, sm, st, prm); break;
-        case 7: launch_dp_r0<7>(wide, (int)grid, warps * 32, sm, st, prm); break;
-        default: launch_dp_r0<15>(wide, (int)grid, warps * 32, sm, st, prm); break;
+        case 1: launch_dp_r0<1, 0>(wide, (int)grid, warps * 32, sm, st, prm); break;
+        case 3: launch_dp_r0<3, 0>(wide, (int)grid, warps * 32, sm, st, prm); break;
+        case 7: launch_dp_r0<7, 0>(wide, (int)grid, warps * 32, sm, st, prm); break;
+        default:
+            if (t.rp == KP_RP_NN) launch_dp_r0<15, KP_RP_NN>(wide, (int)grid, warps * 32, sm, st, prm);
+            else launch_dp_r0<15, 0>(wide, (int)grid, warps * 32, sm, st, prm);
+            break;
         }
         p->launches++;
     }

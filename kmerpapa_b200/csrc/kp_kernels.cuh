@@ -167,7 +167,9 @@ struct KpDpParams {
     uint16_t *flags;            // per row, bit d set = pattern kept whole
 };
 
-template <int R0, bool WIDE>
+// RP: the row pitch as a compile-time constant (0: read it from the tables).  With the pitch known, the tile
+// stride and the four group offsets of a row fold into immediates of the child-tile loads.
+template <int R0, bool WIDE, int RP>
 __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const KpDpParams p)
 {
     typedef typename KpCnt<WIDE>::type C;
@@ -177,8 +179,8 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
     extern __shared__ __align__(16) unsigned char smem[];
     const KpTables &tb = *p.tab;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int rp = tb.rp, nrounds = tb.nrounds, nhigh = tb.nhigh, nrows = tb.nrows;
-    const uint32_t stride = tb.tile_stride, tk = tb.tile_kmers;
+    const int rp = RP ? RP : tb.rp, nrounds = tb.nrounds, nhigh = tb.nhigh, nrows = tb.nrows;
+    const uint32_t stride = RP ? (uint32_t)(NG * RP * 4) : tb.tile_stride, tk = tb.tile_kmers;
     const uint32_t rt_bytes = tb.rt_bytes;
     const int maxhs = tb.maxhs;
 
@@ -261,30 +263,31 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
             const int nchunk = (nrows + 31) >> 5;
             const int nstep = nhs > 0 ? nchunk * nhs : 0;
             float4 xa0[NG], xb0[NG], xa1[NG], xb1[NG];
+            const float4 *tb4 = (const float4 *)tbase;
+            const uint32_t stride4 = stride >> 2;                 // tile stride in float4
             int ls = 0, lrow = lane;          // split and row of the next load
+            const float4 *lptr = tb4 + (lrow < nrows ? lrow : nrows - 1);   // idle lanes of the last chunk re-read a valid row
             int us = 0, urow = lane;          // split and row of the next use
-            int ps = 0, prow = lane;          // split and row of the next L2 prefetch (KP_PF_DIST steps ahead)
-            // register-free deepening of the pipeline: every step also asks L2 for the lines of a later step
+            // register-free deepening of the pipeline: every step also asks L2 for the lines of a later step.
+            // One prefetch per step: the 2 x NG x 4 lines (128 B = 8 rows) of a step map onto the 32 lanes.
+            int ps = 0, pchunk = 0;           // split and first row of the next L2 prefetch (pf_dist steps ahead)
+            const uint32_t *pf_hs = (lane & 16) ? hs2 : hs1;
+            const int pf_g = (lane >> 2) & 3, pf_line = (lane & 3) * 8;
+            const float4 *pf_ptr = tb4 + pf_g * rp + pf_line;
+            const bool pf_on = pf_g < NG;
 #define KP_FL_PREFETCH()                                                                              \
-    if (prow < nrows) {                                                                               \
-        if ((lane & 3) == 0) {                                                                        \
-            const float4 *a_ = (const float4 *)(tbase + (size_t)hs1[ps] * stride) + prow;             \
-            const float4 *b_ = (const float4 *)(tbase + (size_t)hs2[ps] * stride) + prow;             \
-            _Pragma("unroll") for (int g = 0; g < NG; g++) {                                          \
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a_ + g * rp));                          \
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(b_ + g * rp));                          \
-            }                                                                                         \
-        }                                                                                             \
-        if (++ps == nhs) { ps = 0; prow += 32; }                                                      \
+    if (pchunk < nrows) {                                                                             \
+        if (pf_on && pchunk + pf_line < nrows)                                                        \
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_ptr + (size_t)pf_hs[ps] * stride4 + pchunk)); \
+        if (++ps == nhs) { ps = 0; pchunk += 32; }                                                    \
     }
 #define KP_FL_LOAD(xa, xb)                                                                            \
     {                                                                                                 \
         KP_FL_PREFETCH()                                                                              \
-        const int row_ = lrow < nrows ? lrow : nrows - 1;   /* idle lanes of the last chunk re-read a valid row */ \
-        const float4 *a_ = (const float4 *)(tbase + (size_t)hs1[ls] * stride) + row_;                 \
-        const float4 *b_ = (const float4 *)(tbase + (size_t)hs2[ls] * stride) + row_;                 \
+        const float4 *a_ = lptr + (size_t)hs1[ls] * stride4;                                          \
+        const float4 *b_ = lptr + (size_t)hs2[ls] * stride4;                                          \
         _Pragma("unroll") for (int g = 0; g < NG; g++) { xa[g] = __ldg(a_ + g * rp); xb[g] = __ldg(b_ + g * rp); } \
-        if (++ls == nhs) { ls = 0; lrow += 32; }                                                      \
+        if (++ls == nhs) { ls = 0; lrow += 32; lptr = tb4 + (lrow < nrows ? lrow : nrows - 1); }      \
     }
 #define KP_FL_USE(xa, xb)                                                                             \
     {                                                                                                 \

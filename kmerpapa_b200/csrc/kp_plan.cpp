@@ -150,7 +150,7 @@ int kp_build_host_plan(const char *gen_pat, KpHostPlan &P, std::string &err)
         }
     }
     t.nrows = (int32_t)roww;
-    t.rp = (t.nrows + 1) & ~1;
+    t.rp = (t.nrows + 7) & ~7;   // 8 rows = one 128-byte line per float4 group: every group starts on a line
     t.tile_cells = cells;
     t.tile_stride = (uint32_t)(t.ng * t.rp * 4);
     t.tile_kmers = tk;

@@ -28,7 +28,7 @@ struct KpTables {
     int32_t nlow, nhigh;      // low (on-chip) and high (tile) positions
     int32_t estar;            // effective index of the register position (-1: the pattern has no free position)
     int32_t r0, nb0, ng;      // its radix / number of bases / float4 groups per row (1,1,1 when estar < 0)
-    int32_t nrows, rp;        // rows per tile, row pitch (nrows rounded up to even)
+    int32_t nrows, rp;        // rows per tile, row pitch (nrows rounded up to a multiple of 8)
     int32_t nrounds;          // schedule rounds (<= 32 rows each)
     uint32_t tile_cells, tile_stride, tile_kmers;
     uint32_t ntiles;
