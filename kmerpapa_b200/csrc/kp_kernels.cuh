@@ -126,6 +126,14 @@ template <int R0> __device__ __forceinline__ unsigned kp_bm(int d)
     return R0 == 15 ? kpc_bm15[d] : (R0 == 7 ? kpc_bm7[d] : (R0 == 3 ? kpc_bm3[d] : kpc_bm1[d]));
 }
 
+// min(a, b, c) in one instruction (FMNMX3, sm_100); the same value as fminf(fminf(a, b), c)
+__device__ __forceinline__ float kp_min3(float a, float b, float c)
+{
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 // Float32 lower bound of the self-score (w_numba.py:56-61) for the score filter, two patterns at a time with
 // the packed f32x2 instructions of sm_100 (FADD2/FMUL2/FFMA2).  The estimate's relative error is < 1e-5 (fast
 // log: < 2^-21 absolute; log(1-p) by its series below p = 2^-5; no cancellation: both terms are >= 0); the bound
@@ -342,18 +350,39 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
                     v[4 * g] = x.x; v[4 * g + 1] = x.y; v[4 * g + 2] = x.z; v[4 * g + 3] = x.w;
                 }
                 // ---- cross-row splits: finished rows of this tile, shared memory ----
-                for (int i = xs_off[srow]; i < xs_off[srow + 1]; i++) {
-                    const uint32_t pr = xs[i];
-                    const float4 *a = S + (pr & 0xFFFFu), *b = S + (pr >> 16);
+                {
+                    int i = xs_off[srow];
+                    const int iend = xs_off[srow + 1];
+                    for (; i + 2 <= iend; i += 2) {   // two splits per pass: one 3-input min per cell
+                        const uint32_t pr = xs[i], pq = xs[i + 1];
+                        const float4 *a = S + (pr & 0xFFFFu), *b = S + (pr >> 16);
+                        const float4 *c = S + (pq & 0xFFFFu), *e = S + (pq >> 16);
 #pragma unroll
-                    for (int g = 0; g < NG; g++) {
-                        float4 xa = a[g * rp], xb = b[g * rp];
-                        const float2 lo_ = __fadd2_rn(make_float2(xa.x, xa.y), make_float2(xb.x, xb.y));
-                        const float2 hi_ = __fadd2_rn(make_float2(xa.z, xa.w), make_float2(xb.z, xb.w));
-                        v[4 * g + 0] = fminf(v[4 * g + 0], lo_.x);
-                        v[4 * g + 1] = fminf(v[4 * g + 1], lo_.y);
-                        v[4 * g + 2] = fminf(v[4 * g + 2], hi_.x);
-                        v[4 * g + 3] = fminf(v[4 * g + 3], hi_.y);
+                        for (int g = 0; g < NG; g++) {
+                            const float4 xa = a[g * rp], xb = b[g * rp], xc = c[g * rp], xe = e[g * rp];
+                            const float2 l1 = __fadd2_rn(make_float2(xa.x, xa.y), make_float2(xb.x, xb.y));
+                            const float2 h1 = __fadd2_rn(make_float2(xa.z, xa.w), make_float2(xb.z, xb.w));
+                            const float2 l2 = __fadd2_rn(make_float2(xc.x, xc.y), make_float2(xe.x, xe.y));
+                            const float2 h2 = __fadd2_rn(make_float2(xc.z, xc.w), make_float2(xe.z, xe.w));
+                            v[4 * g + 0] = kp_min3(v[4 * g + 0], l1.x, l2.x);
+                            v[4 * g + 1] = kp_min3(v[4 * g + 1], l1.y, l2.y);
+                            v[4 * g + 2] = kp_min3(v[4 * g + 2], h1.x, h2.x);
+                            v[4 * g + 3] = kp_min3(v[4 * g + 3], h1.y, h2.y);
+                        }
+                    }
+                    if (i < iend) {
+                        const uint32_t pr = xs[i];
+                        const float4 *a = S + (pr & 0xFFFFu), *b = S + (pr >> 16);
+#pragma unroll
+                        for (int g = 0; g < NG; g++) {
+                            const float4 xa = a[g * rp], xb = b[g * rp];
+                            const float2 lo_ = __fadd2_rn(make_float2(xa.x, xa.y), make_float2(xb.x, xb.y));
+                            const float2 hi_ = __fadd2_rn(make_float2(xa.z, xa.w), make_float2(xb.z, xb.w));
+                            v[4 * g + 0] = fminf(v[4 * g + 0], lo_.x);
+                            v[4 * g + 1] = fminf(v[4 * g + 1], lo_.y);
+                            v[4 * g + 2] = fminf(v[4 * g + 2], hi_.x);
+                            v[4 * g + 3] = fminf(v[4 * g + 3], hi_.y);
+                        }
                     }
                 }
                 // ---- counts of this row at the single-nucleotide digits of the register position ----
@@ -361,9 +390,17 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
 #pragma unroll
                 for (int b = 0; b < NB; b++) { m[b] = 0; u[b] = 0; }
                 for (int i = bs_off[srow]; i < bs_off[srow + 1]; i++) {
-                    const C *q = bc + (size_t)bs[i] * NB * 2;
+                    const C *q = bc + (size_t)bs[i] * NB * 2;   // {M, U} of the NB k-mers of a base row: NB * 2 * sizeof(C) bytes
+                    if (!WIDE && NB % 2 == 0) {                 // 16-byte aligned: two k-mers per load
 #pragma unroll
-                    for (int b = 0; b < NB; b++) { m[b] += q[b * 2 + 0]; u[b] += q[b * 2 + 1]; }
+                        for (int b = 0; b < NB; b += 2) {
+                            const uint4 x = *(const uint4 *)(q + b * 2);
+                            m[b] += x.x; u[b] += x.y; m[b + 1] += x.z; u[b + 1] += x.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < NB; b++) { m[b] += q[b * 2 + 0]; u[b] += q[b * 2 + 1]; }
+                    }
                 }
                 // ---- score filter: which patterns can still be kept whole? (v only decreases from here) ----
                 const bool leafrow = p.leaf_wave && row_level[srow] == 0;
@@ -417,6 +454,7 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
         if (sf_ < v[D] || (sf_ == v[D] && ((rupm >> (D)) & 1u))) { v[D] = sf_; flag |= 1u << (D); }   \
     }
 #define KP_SP(D, A, B) v[D] = fminf(v[D], __fadd_rn(v[A], v[B]));
+#define KP_SP2(D, A, B, A2, B2) v[D] = kp_min3(v[D], __fadd_rn(v[A], v[B]), __fadd_rn(v[A2], v[B2]));
                 if (R0 == 1) {
                     KP_FIN(0)
                 } else if (R0 == 3) {
@@ -427,7 +465,7 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
                     KP_SP(3, 0, 1) KP_FIN(3)
                     KP_SP(4, 0, 2) KP_FIN(4)
                     KP_SP(5, 1, 2) KP_FIN(5)
-                    KP_SP(6, 0, 5) KP_SP(6, 1, 4) KP_SP(6, 2, 3) KP_FIN(6)
+                    KP_SP2(6, 0, 5, 1, 4) KP_SP(6, 2, 3) KP_FIN(6)
                 } else {
                     KP_FIN(0) KP_FIN(1) KP_FIN(2) KP_FIN(3)
                     KP_SP(4, 0, 2) KP_FIN(4)     // R = A|G
@@ -436,15 +474,16 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
                     KP_SP(7, 0, 3) KP_FIN(7)     // W = A|T
                     KP_SP(8, 2, 3) KP_FIN(8)     // K = G|T
                     KP_SP(9, 0, 1) KP_FIN(9)     // M = A|C
-                    KP_SP(10, 1, 8) KP_SP(10, 2, 5) KP_SP(10, 3, 6) KP_FIN(10)   // B
-                    KP_SP(11, 0, 8) KP_SP(11, 2, 7) KP_SP(11, 3, 4) KP_FIN(11)   // D
-                    KP_SP(12, 0, 5) KP_SP(12, 1, 7) KP_SP(12, 3, 9) KP_FIN(12)   // H
-                    KP_SP(13, 0, 6) KP_SP(13, 1, 4) KP_SP(13, 2, 9) KP_FIN(13)   // V
-                    KP_SP(14, 6, 7) KP_SP(14, 8, 9) KP_SP(14, 4, 5) KP_SP(14, 0, 10)
-                    KP_SP(14, 1, 11) KP_SP(14, 2, 12) KP_SP(14, 3, 13) KP_FIN(14)  // N
+                    KP_SP2(10, 1, 8, 2, 5) KP_SP(10, 3, 6) KP_FIN(10)   // B
+                    KP_SP2(11, 0, 8, 2, 7) KP_SP(11, 3, 4) KP_FIN(11)   // D
+                    KP_SP2(12, 0, 5, 1, 7) KP_SP(12, 3, 9) KP_FIN(12)   // H
+                    KP_SP2(13, 0, 6, 1, 4) KP_SP(13, 2, 9) KP_FIN(13)   // V
+                    KP_SP2(14, 6, 7, 8, 9) KP_SP2(14, 4, 5, 0, 10)
+                    KP_SP2(14, 1, 11, 2, 12) KP_SP(14, 3, 13) KP_FIN(14)  // N
                 }
 #undef KP_FIN
 #undef KP_SP
+#undef KP_SP2
                 // ---- store the row ----
 #pragma unroll
                 for (int c = R0; c < NG * 4; c++) v[c] = 0.f;
