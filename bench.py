@@ -51,7 +51,7 @@ class ClockSampler:
 
     REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index, period_s=0.1):
+    def __init__(self, index, period_s=0.025):
         self.rows, self.period, self.running, self.thread = [], period_s, False, None
         self.handle = None
         try:
@@ -338,7 +338,7 @@ def bench_cv(args, rank, world, local, steps=None, warmup=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
