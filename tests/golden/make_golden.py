@@ -166,9 +166,18 @@ def worker_cli(spec_path, out_path):
     argv += ["-o", out_file]
     if spec.get("cvfile", True):
         argv += ["--CVfile", cv_file]
+    if spec.get("zero_empty"):
+        # tiny CV tables (here the 3-mers of --test_smaller_k) come from recycled heap memory in the reference
+        # and its fold totals then depend on that garbage; zero pages are what large runs see
+        import numpy as np
+
+        real_empty = np.empty
+        np.empty = lambda shape, dtype=float, **k: np.zeros(shape, dtype=dtype)
     err = io.StringIO()
     with contextlib.redirect_stderr(err):
         rc = cli.main(argv)
+    if spec.get("zero_empty"):
+        np.empty = real_empty
     import gc
 
     gc.collect()   # cli.main leaves its output files to the garbage collector: make sure they are flushed
@@ -275,9 +284,42 @@ def copy_test_data():
         shutil.copy(os.path.join(REF_DATA, f), os.path.join(HERE, "data", f))
 
 
+def derive_inputs():
+    """Input files for the other accepted formats, derived from the 5-mer test data:
+    negative_5mers.txt (background - positive) and joint_5mers.txt (kmer positive background)."""
+    d = os.path.join(HERE, "data")
+    pos, bg = {}, {}
+    for name, tab in (("mutated_5mers.txt", pos), ("background_5mers.txt", bg)):
+        for line in open(os.path.join(d, name)):
+            kmer, count = line.split()
+            tab[kmer] = tab.get(kmer, 0) + int(count)
+    with open(os.path.join(d, "negative_5mers.txt"), "w") as f:
+        for kmer in sorted(bg):
+            f.write(f"{kmer} {bg[kmer] - pos.get(kmer, 0)}\n")
+    with open(os.path.join(d, "joint_5mers.txt"), "w") as f:
+        for kmer in sorted(bg):
+            f.write(f"{kmer}\t{pos.get(kmer, 0)}\t{bg[kmer]}\n")
+
+
 def make_cli(which):
     d = os.path.join(HERE, "data")
-    if which == "cli5":   # BASELINE config 1
+    if which == "cli5_negative":   # --negative instead of --background
+        argv = ["-p", f"{d}/mutated_5mers.txt", "-n", f"{d}/negative_5mers.txt", "-c", "5", "-a", "0.8"]
+        run_worker("cli", {"argv": argv, "cvfile": False}, os.path.join(HERE, "cli_5mers_negative.json"))
+    elif which == "cli5_joint":    # --joint_context_counts, long output
+        argv = ["-j", f"{d}/joint_5mers.txt", "-c", "4", "-a", "2", "-l"]
+        run_worker("cli", {"argv": argv, "cvfile": False}, os.path.join(HERE, "cli_5mers_joint.json"))
+    elif which == "cli5_trim":     # 7-mer background collapsed around its centre to the 5-mers of the positive set
+        argv = ["-p", f"{d}/mutated_5mers.txt", "-b", f"{d}/background_7mers.txt", "-c", "5", "-a", "0.8"]
+        run_worker("cli", {"argv": argv, "cvfile": False}, os.path.join(HERE, "cli_5mers_trimmed_background.json"))
+    elif which == "cli5_smallerk":  # --test_smaller_k: CV on 5-mers and on 3-mers, final DP on the better k
+        argv = ["-p", f"{d}/mutated_5mers.txt", "-b", f"{d}/background_5mers.txt", "-c", "3", "6", "--test_smaller_k",
+                "--seed", "2"]
+        run_worker("cli", {"argv": argv, "zero_empty": True}, os.path.join(HERE, "cli_5mers_smaller_k.json"))
+    elif which == "cli5_scores":   # the information-criterion penalties (--score BIC)
+        argv = ["-p", f"{d}/mutated_5mers.txt", "-b", f"{d}/background_5mers.txt", "--score", "BIC", "-a", "1"]
+        run_worker("cli", {"argv": argv, "cvfile": False}, os.path.join(HERE, "cli_5mers_BIC.json"))
+    elif which == "cli5":   # BASELINE config 1
         argv = ["-p", f"{d}/mutated_5mers.txt", "-b", f"{d}/background_5mers.txt", "-c", "3", "5", "7", "--seed", "1"]
         run_worker("cli", {"argv": argv}, os.path.join(HERE, "cli_cfg1_5mers.json"))
     elif which == "cli5_single":
@@ -302,11 +344,13 @@ def main():
         return
     what = sys.argv[1:] or ["all"]
     copy_test_data()
+    derive_inputs()
     for w in what:
         if w in ("all", "small"):
             make_small()
         if w == "all":
-            for c in ("cli5", "cli5_single", "cli5_sp", "cli7_single", "cli7"):
+            for c in ("cli5", "cli5_single", "cli5_sp", "cli5_negative", "cli5_joint", "cli5_trim", "cli5_smallerk",
+                      "cli5_scores", "cli7_single", "cli7"):
                 make_cli(c)
         elif w.startswith("cli"):
             make_cli(w)
