@@ -259,9 +259,15 @@ int kp_expand_counts(kp_plan *p, const int64_t *d_kmerM, const int64_t *d_kmerU,
     kp_expand_base_kernel<<<grid_for(p->host.nkmer, 256, p->sm_count), 256, 0, st>>>(
         p->d_tab, p->host.nkmer, (const long long *)d_kmerM, (const long long *)d_kmerU, (long long *)d_expM, (long long *)d_expU);
     p->launches++;
-    uint64_t total = (uint64_t)t.ntiles * t.tile_kmers;
     for (int hi = 0; hi < t.nhigh; hi++) {
-        kp_expand_pass_kernel<<<grid_for(total, 256, p->sm_count), 256, 0, st>>>(p->d_tab, hi, (long long *)d_expM, (long long *)d_expU);
+        uint64_t total = t.tile_kmers;   // elements this pass writes
+        for (int h = 0; h < t.nhigh; h++) {
+            const int f = t.highpos[h];
+            total *= h < hi ? (uint64_t)t.radix[f] : (h == hi ? (uint64_t)(t.radix[f] - t.nbase[f]) : (uint64_t)t.nbase[f]);
+        }
+        if (total == 0) continue;
+        kp_expand_pass_kernel<<<grid_for(total, 256, p->sm_count), 256, 0, st>>>(p->d_tab, hi, total, (long long *)d_expM,
+                                                                                 (long long *)d_expU);
         p->launches++;
     }
     KP_CUDA(cudaGetLastError());

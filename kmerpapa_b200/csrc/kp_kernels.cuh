@@ -563,38 +563,39 @@ __global__ void kp_expand_base_kernel(const KpTables *tab, unsigned long long nk
     }
 }
 
-// pass over the hi-th high position: tiles whose digit there is multi-letter and whose later high digits are single
-__global__ void kp_expand_pass_kernel(const KpTables *tab, int hi, long long *expM, long long *expU)
+// pass over the hi-th high position: tiles whose digit there is multi-letter, whose earlier high digits are anything
+// (already expanded) and whose later high digits are single nucleotides.  Only those `total` elements are enumerated.
+__global__ void kp_expand_pass_kernel(const KpTables *tab, int hi, unsigned long long total, long long *expM, long long *expU)
 {
     const KpTables &tb = *tab;
     const uint32_t tk = tb.tile_kmers;
-    const unsigned long long total = (unsigned long long)tb.ntiles * tk;
     const int e = tb.highpos[hi];
-    const uint32_t hw = tb.highw[e], rad = tb.radix[e], nb = tb.nbase[e];
+    const uint32_t hw = tb.highw[e];
     for (unsigned long long x = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; x < total;
          x += (unsigned long long)gridDim.x * blockDim.x) {
-        uint32_t tile = (uint32_t)(x / tk), kl = (uint32_t)(x % tk);
-        uint32_t rest = tile / hw;
-        uint32_t d = rest % rad;
-        if (d < nb) continue;
-        rest /= rad;
-        bool ok = true;
-        for (int h = hi + 1; h < tb.nhigh; h++) {
-            int f = tb.highpos[h];
-            if (rest % tb.radix[f] >= tb.nbase[f]) { ok = false; break; }
-            rest /= tb.radix[f];
+        const uint32_t kl = (uint32_t)(x % tk);
+        unsigned long long r = x / tk;
+        uint32_t tile = 0, d = 0;
+        for (int h = 0; h < tb.nhigh; h++) {
+            const int f = tb.highpos[h];
+            const uint32_t nb = tb.nbase[f];
+            const uint32_t n = h < hi ? tb.radix[f] : (h == hi ? tb.radix[f] - nb : nb);
+            uint32_t dig = (uint32_t)(r % n);   // a single-nucleotide digit is its base index
+            r /= n;
+            if (h == hi) { dig += nb; d = dig; }
+            tile += dig * tb.highw[f];
         }
-        if (!ok) continue;
-        uint32_t m = tb.digit_mask[e][d];
+        const uint32_t m = tb.digit_mask[e][d];
         long long am = 0, au = 0;
         for (int b = 0; b < 4; b++) {
             if (!((m >> b) & 1u)) continue;
-            size_t src = (size_t)(tile - (d - tb.mask_digit[e][1u << b]) * hw) * tk + kl;
+            const size_t src = (size_t)(tile - (d - tb.mask_digit[e][1u << b]) * hw) * tk + kl;
             am += expM[src];
             au += expU[src];
         }
-        expM[x] = am;
-        expU[x] = au;
+        const size_t dst = (size_t)tile * tk + kl;
+        expM[dst] = am;
+        expU[dst] = au;
     }
 }
 
@@ -730,8 +731,26 @@ __global__ void __launch_bounds__(256) kp_backtrack_level_kernel(const KpTables 
     const unsigned long long nw = (unsigned long long)gridDim.x * (blockDim.x >> 5);
     for (unsigned long long i = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < ncur; i += nw) {
         KpBtNode nd = cur[i];
-        KpLoc L = kp_locate_dev(tb, srow_of_row, nd.pat);
+        // location of the node; its children differ in one digit, so they are located by a delta (no divisions)
+        unsigned long long ntile = 0;
+        uint32_t nrow = 0, nd0 = 0;
+        for (int e = 0; e < tb.npos; e++) {
+            uint32_t dig = (uint32_t)((nd.pat / tb.extw[e]) % tb.radix[e]);
+            if (e == tb.estar) nd0 = dig;
+            else if (tb.is_low[e]) nrow += dig * tb.roww[e];
+            else ntile += (unsigned long long)dig * tb.highw[e];
+        }
+        KpLoc L;
+        L.tile = ntile; L.d0 = nd0; L.srow = srow_of_row[nrow];
         bool kept = (flags[L.tile * tb.rp + L.srow] >> L.d0) & 1u;
+        auto child_best = [&](int e, int d, int c) -> float {
+            unsigned long long ct = ntile;
+            uint32_t cr = nrow, cd = nd0;
+            if (e == tb.estar) cd = (uint32_t)c;
+            else if (tb.is_low[e]) cr -= (uint32_t)(d - c) * tb.roww[e];
+            else ct -= (unsigned long long)(d - c) * tb.highw[e];
+            return best[ct * tb.tile_stride + ((size_t)(cd >> 2) * tb.rp + srow_of_row[cr]) * 4 + (cd & 3)];
+        };
         float bv = __int_as_float(0x7f800000);
         int code = 0x7fffffff;
         unsigned long long b1 = 0, b2 = 0;
@@ -747,8 +766,7 @@ __global__ void __launch_bounds__(256) kp_backtrack_level_kernel(const KpTables 
                 v[j] = __int_as_float(0x7f800000);
                 if (j < ns) {
                     int c1 = tb.mask_digit[e][tb.ms_c1[m][j]], c2 = tb.mask_digit[e][tb.ms_c2[m][j]];
-                    v[j] = __fadd_rn(kp_best_at(tb, srow_of_row, best, nd.pat - (unsigned long long)(d - c1) * w),
-                                     kp_best_at(tb, srow_of_row, best, nd.pat - (unsigned long long)(d - c2) * w));
+                    v[j] = __fadd_rn(child_best(e, d, c1), child_best(e, d, c2));
                 }
             }
 #pragma unroll
