@@ -148,6 +148,57 @@ int kp_pattern_offset(const kp_plan *plan, uint64_t patnum, uint64_t *table_elem
 /* Number of kernel launches issued through this plan so far (for bench.py's gpu_launches). */
 uint64_t kp_plan_launch_count(const kp_plan *plan);
 
+/* ---------------------------------------------------------------------------------------------------
+ * One DP sharded over the GPUs of a node (pattern-space sharding; the reference has no
+ * counterpart, its tables are single numpy arrays, bottum_up_array_w_numba.py:82-91).
+ *
+ * The score table is split by the digit of the TOP high position of the tile number; every rank (one process per
+ * GPU, or several shards in one process) owns the tiles of its digits and runs the same waves on them.  The
+ * children of a tile along the top position may live on a peer: the DP kernel loads them from the peer's memory
+ * (NVLink) in the same pipeline as the local ones.  The caller synchronises the ranks between waves
+ * (torch.distributed barrier / all_reduce on the same stream) and provides every rank with the FULL expanded
+ * count tables (kp_expand_counts is cheap and replicated).
+ *
+ *   kp_shard_create -> exchange pointers (kp_ipc_export / all_gather / kp_ipc_open, or directly within one
+ *   process) -> kp_shard_set_peer for every other rank -> for wave in 0..nwaves-1: kp_shard_dp_wave, barrier ->
+ *   kp_shard_backtrack / kp_shard_gather on any rank.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct kp_shard kp_shard;
+
+typedef struct kp_shard_info {
+    uint64_t local_tiles;   /* tiles stored on this rank */
+    uint64_t table_elems;   /* float32 elements of this rank's score shard */
+    uint64_t kept_elems;    /* uint16 elements of this rank's kept-whole shard */
+    uint64_t d_best;        /* device pointer of the score shard (cudaMalloc: exportable with kp_ipc_export) */
+    uint64_t d_kept;        /* device pointer of the kept-whole shard */
+    uint32_t rank, world;
+    uint32_t nwaves;        /* waves of the DP (the same on every rank) */
+    uint32_t top_digits;    /* digits of the top high position owned by this rank */
+} kp_shard_info;
+
+/* owner rank and local slot of every digit of the top high position (16 entries each) for `world` ranks */
+int kp_shard_assignment(const kp_plan *plan, int world, uint8_t *owner16, uint8_t *slot16);
+/* allocate this rank's shard on the plan's device; world <= min(8, radix of the top position); needs an N position */
+int kp_shard_create(kp_plan *plan, int rank, int world, kp_shard **out);
+int kp_shard_destroy(kp_shard *shard);
+int kp_shard_get_info(const kp_shard *shard, kp_shard_info *out);
+/* device pointers (valid on this rank's device: peer-mapped) of rank `peer`'s shard */
+int kp_shard_set_peer(kp_shard *shard, int peer, const float *d_best, const uint16_t *d_kept);
+/* CUDA IPC plumbing: 64-byte handle of a cudaMalloc allocation; map / unmap a peer's allocation on `device` */
+int kp_ipc_export(const void *d_ptr, uint8_t *handle64);
+int kp_ipc_open(int device, const uint8_t *handle64, void **d_ptr);
+int kp_ipc_close(int device, void *d_ptr);
+/* this rank's tiles of one wave (same arguments as kp_dp_single; d_expM/d_expU are the full expanded tables).
+ * All ranks must have finished wave w-1 before any rank starts wave w. */
+int kp_shard_dp_wave(kp_shard *shard, int wave, const int64_t *d_expM, const int64_t *d_expU, uint64_t max_count,
+                     double alpha, double beta, double penalty, void *stream);
+/* like kp_backtrack, over all shards (reads peers' memory); callable on any rank after the last wave */
+int kp_shard_backtrack(kp_shard *shard, void *d_ws, uint64_t cap, uint64_t root, uint64_t *h_patnums, uint64_t *n_out,
+                       void *stream);
+/* score / kept-whole flag / split code (any of the outputs may be NULL) of arbitrary patterns, from any shard */
+int kp_shard_gather(kp_shard *shard, const uint64_t *h_patnums, uint64_t n, float *h_best, uint8_t *h_kept,
+                    uint8_t *h_codes, void *stream);
+
 /* Test hook: y[i] = device log(x[i]) (the glibc-exact restatement used by the scoring kernels). */
 int kp_debug_log(int device, const double *h_x, double *h_y, uint64_t n);
 /* Test hook: level-0 score of (M,U) pairs on the device (scipy xlogy/xlog1py restated). */

@@ -23,6 +23,14 @@ class PlanInfo(ctypes.Structure):
     ]
 
 
+class ShardInfo(ctypes.Structure):
+    _fields_ = [
+        ("local_tiles", ctypes.c_uint64), ("table_elems", ctypes.c_uint64), ("kept_elems", ctypes.c_uint64),
+        ("d_best", ctypes.c_uint64), ("d_kept", ctypes.c_uint64),
+        ("rank", ctypes.c_uint32), ("world", ctypes.c_uint32), ("nwaves", ctypes.c_uint32), ("top_digits", ctypes.c_uint32),
+    ]
+
+
 # every symbol include/kmerpapa_b200.h declares: name -> (restype, argtypes)
 _vp, _u64, _i64, _dbl, _int, _cp = (ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64, ctypes.c_double, ctypes.c_int,
                                    ctypes.c_char_p)
@@ -45,6 +53,17 @@ SYMBOLS = {
     "kp_pattern_counts": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp]),
     "kp_pattern_offset": (_int, [_vp, _u64, ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(ctypes.c_uint32)]),
     "kp_plan_launch_count": (_u64, [_vp]),
+    "kp_shard_assignment": (_int, [_vp, _int, _vp, _vp]),
+    "kp_shard_create": (_int, [_vp, _int, _int, ctypes.POINTER(_vp)]),
+    "kp_shard_destroy": (_int, [_vp]),
+    "kp_shard_get_info": (_int, [_vp, ctypes.POINTER(ShardInfo)]),
+    "kp_shard_set_peer": (_int, [_vp, _int, _vp, _vp]),
+    "kp_ipc_export": (_int, [_vp, _vp]),
+    "kp_ipc_open": (_int, [_int, _vp, ctypes.POINTER(_vp)]),
+    "kp_ipc_close": (_int, [_int, _vp]),
+    "kp_shard_dp_wave": (_int, [_vp, _int, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp]),
+    "kp_shard_backtrack": (_int, [_vp, _vp, _u64, _u64, _vp, ctypes.POINTER(_u64), _vp]),
+    "kp_shard_gather": (_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp]),
     "kp_debug_log": (_int, [_int, _vp, _vp, _u64]),
     "kp_debug_leaf_score": (_int, [_int, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp]),
 }

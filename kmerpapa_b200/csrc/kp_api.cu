@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -55,20 +56,32 @@ template <bool WIDE>
 static const void *dp_kernel_for_radix(int r0, int rp)
 {
     switch (r0) {
-    case 1: return (const void *)kp_dp_rows_kernel<1, WIDE, 0>;
-    case 3: return (const void *)kp_dp_rows_kernel<3, WIDE, 0>;
-    case 7: return (const void *)kp_dp_rows_kernel<7, WIDE, 0>;
+    case 1: return (const void *)kp_dp_rows_kernel<1, WIDE, 0, false>;
+    case 3: return (const void *)kp_dp_rows_kernel<3, WIDE, 0, false>;
+    case 7: return (const void *)kp_dp_rows_kernel<7, WIDE, 0, false>;
     default:
-        return rp == KP_RP_NN ? (const void *)kp_dp_rows_kernel<15, WIDE, KP_RP_NN> : (const void *)kp_dp_rows_kernel<15, WIDE, 0>;
+        return rp == KP_RP_NN ? (const void *)kp_dp_rows_kernel<15, WIDE, KP_RP_NN, false>
+                              : (const void *)kp_dp_rows_kernel<15, WIDE, 0, false>;
     }
 }
 
-template <int R0, int RP>
+template <int R0, int RP, bool SHARDED>
 static void launch_dp_r0(bool wide, int grid, int threads, size_t smem, cudaStream_t st, const KpDpParams &prm)
 {
-    if (wide) kp_dp_rows_kernel<R0, true, RP><<<grid, threads, smem, st>>>(prm);
-    else kp_dp_rows_kernel<R0, false, RP><<<grid, threads, smem, st>>>(prm);
+    if (wide) kp_dp_rows_kernel<R0, true, RP, SHARDED><<<grid, threads, smem, st>>>(prm);
+    else kp_dp_rows_kernel<R0, false, RP, SHARDED><<<grid, threads, smem, st>>>(prm);
 }
+
+// the sharded DP exists for the register radix 15 only (a pattern without an N position is far too small to shard)
+template <bool WIDE>
+static const void *dp_kernel_sharded(int rp)
+{
+    return rp == KP_RP_NN ? (const void *)kp_dp_rows_kernel<15, WIDE, KP_RP_NN, true>
+                          : (const void *)kp_dp_rows_kernel<15, WIDE, 0, true>;
+}
+
+// a view of one unsharded table
+static KpView single_view(const kp_plan *p, const float *best, const uint16_t *flags);
 
 // float32 sum of the leaves' held-out losses in the order of the partition tree (keys sorted ascending;
 // bit 63-depth of a key tells the side taken at that depth)
@@ -85,6 +98,16 @@ static float tree_sum(const unsigned long long *keys, const float *vals, size_t 
     volatile float l = tree_sum(keys, vals, lo, a, depth + 1), r = tree_sum(keys, vals, a, hi, depth + 1);
     volatile float sum = l + r;   // float32 add, like the reference's test_score_mem row sums
     return sum;
+}
+
+static KpView single_view(const kp_plan *p, const float *best, const uint16_t *flags)
+{
+    KpView v;
+    memset(&v, 0, sizeof v);
+    v.best[0] = best;
+    v.flags[0] = flags;
+    v.hw_top = (uint32_t)p->host.t.ntiles;   // tile / hw_top == 0 for every tile
+    return v;
 }
 
 extern "C" {
@@ -299,12 +322,12 @@ static int launch_dp(kp_plan *p, bool wide, KpDpParams prm, cudaStream_t st)
         if (grid > (uint64_t)p->sm_count) grid = p->sm_count;
         size_t sm = 2048 + t.rt_bytes + (size_t)warps * t.warp_smem_bytes[wide];
         switch (t.r0) {
-        case 1: launch_dp_r0<1, 0>(wide, (int)grid, warps * 32, sm, st, prm); break;
-        case 3: launch_dp_r0<3, 0>(wide, (int)grid, warps * 32, sm, st, prm); break;
-        case 7: launch_dp_r0<7, 0>(wide, (int)grid, warps * 32, sm, st, prm); break;
+        case 1: launch_dp_r0<1, 0, false>(wide, (int)grid, warps * 32, sm, st, prm); break;
+        case 3: launch_dp_r0<3, 0, false>(wide, (int)grid, warps * 32, sm, st, prm); break;
+        case 7: launch_dp_r0<7, 0, false>(wide, (int)grid, warps * 32, sm, st, prm); break;
         default:
-            if (t.rp == KP_RP_NN) launch_dp_r0<15, KP_RP_NN>(wide, (int)grid, warps * 32, sm, st, prm);
-            else launch_dp_r0<15, 0>(wide, (int)grid, warps * 32, sm, st, prm);
+            if (t.rp == KP_RP_NN) launch_dp_r0<15, KP_RP_NN, false>(wide, (int)grid, warps * 32, sm, st, prm);
+            else launch_dp_r0<15, 0, false>(wide, (int)grid, warps * 32, sm, st, prm);
             break;
         }
         p->launches++;
@@ -334,7 +357,7 @@ int kp_dp_single(kp_plan *p, const int64_t *d_expM, const int64_t *d_expU, uint6
 }
 
 // breadth-first backtrack from `root`; leaves end up sorted by path key in the workspace
-static int backtrack_device(kp_plan *p, const float *d_best, const uint16_t *d_kept, void *d_ws, uint64_t cap, uint64_t root,
+static int backtrack_device(kp_plan *p, const KpView &vw, void *d_ws, uint64_t cap, uint64_t root,
                             cudaStream_t st, unsigned long long **sorted_out, unsigned long long **keys_out, float **vals_out,
                             unsigned long long **ctr_out)
 {
@@ -348,7 +371,7 @@ static int backtrack_device(kp_plan *p, const float *d_best, const uint16_t *d_k
     int grid = (int)((cap + 7) / 8);
     if (grid > p->sm_count * 2) grid = p->sm_count * 2;
     for (int d = 0; d < levels && d < 64; d++) {
-        kp_backtrack_level_kernel<<<grid, 256, 0, st>>>(p->d_tab, p->d_rowtab, d_best, d_kept, d, (d & 1) ? fb : fa,
+        kp_backtrack_level_kernel<<<grid, 256, 0, st>>>(p->d_tab, p->d_rowtab, vw, d, (d & 1) ? fb : fa,
                                                         (d & 1) ? fa : fb, leaves, cap, ctr);
         p->launches++;
     }
@@ -370,7 +393,7 @@ int kp_backtrack(kp_plan *p, const float *d_best, const uint16_t *d_kept, void *
     KP_CUDA(cudaSetDevice(p->device));
     unsigned long long *sorted, *keys, *ctr;
     float *vals;
-    if (backtrack_device(p, d_best, d_kept, d_ws, cap, root, st, &sorted, &keys, &vals, &ctr)) return 1;
+    if (backtrack_device(p, single_view(p, d_best, d_kept), d_ws, cap, root, st, &sorted, &keys, &vals, &ctr)) return 1;
     unsigned long long hc[2] = {0, 0};
     KP_CUDA(cudaMemcpyAsync(hc, ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaStreamSynchronize(st));
@@ -392,7 +415,7 @@ int kp_cv_heldout(kp_plan *p, const float *d_train, const uint16_t *d_kept, cons
     KP_CUDA(cudaSetDevice(p->device));
     unsigned long long *sorted, *keys, *ctr;
     float *vals;
-    if (backtrack_device(p, d_train, d_kept, d_ws, cap, root, st, &sorted, &keys, &vals, &ctr)) return 1;
+    if (backtrack_device(p, single_view(p, d_train, d_kept), d_ws, cap, root, st, &sorted, &keys, &vals, &ctr)) return 1;
     kp_cv_leaf_kernel<<<p->sm_count, 128, 0, st>>>(p->d_tab, p->d_rowtab, (const long long *)d_expMtr, (const long long *)d_expUtr,
                                                    (const long long *)d_expMtest, (const long long *)d_expUtest, alpha, beta_fold,
                                                    penalty, sorted, ctr, cap, vals);
@@ -452,7 +475,7 @@ int kp_split_codes(kp_plan *p, const float *d_best, const uint16_t *d_kept, cons
     unsigned long long *d_pat = (unsigned long long *)p->d_scratch;
     uint8_t *d_codes = (uint8_t *)(d_pat + n);
     KP_CUDA(cudaMemcpyAsync(d_pat, h_patnums, n * 8, cudaMemcpyHostToDevice, st));
-    kp_split_codes_kernel<<<grid_for(n, 256, p->sm_count), 256, 0, st>>>(p->d_tab, p->d_rowtab, d_best, d_kept, d_pat, n, d_codes);
+    kp_split_codes_kernel<<<grid_for(n, 256, p->sm_count), 256, 0, st>>>(p->d_tab, p->d_rowtab, single_view(p, d_best, d_kept), d_pat, n, d_codes);
     p->launches++;
     KP_CUDA(cudaGetLastError());
     KP_CUDA(cudaMemcpyAsync(h_codes, d_codes, n, cudaMemcpyDeviceToHost, st));
@@ -468,7 +491,7 @@ int kp_gather_table(kp_plan *p, const float *d_table, uint64_t first, uint64_t n
     KP_CUDA(cudaSetDevice(p->device));
     if (scratch_reserve(p, n * 4, st)) return 1;
     float *d_out = (float *)p->d_scratch;
-    kp_gather_kernel<<<grid_for(n, 256, p->sm_count), 256, 0, st>>>(p->d_tab, p->d_rowtab, d_table, nullptr, first, n, d_out);
+    kp_gather_kernel<<<grid_for(n, 256, p->sm_count), 256, 0, st>>>(p->d_tab, p->d_rowtab, single_view(p, d_table, nullptr), nullptr, first, n, d_out);
     p->launches++;
     KP_CUDA(cudaGetLastError());
     KP_CUDA(cudaMemcpyAsync(h_out, d_out, n * 4, cudaMemcpyDeviceToHost, st));
@@ -484,7 +507,7 @@ int kp_gather_kept(kp_plan *p, const uint16_t *d_kept, uint64_t first, uint64_t 
     KP_CUDA(cudaSetDevice(p->device));
     if (scratch_reserve(p, n, st)) return 1;
     uint8_t *d_out = (uint8_t *)p->d_scratch;
-    kp_gather_flags_kernel<<<grid_for(n, 256, p->sm_count), 256, 0, st>>>(p->d_tab, p->d_rowtab, d_kept, first, n, d_out);
+    kp_gather_flags_kernel<<<grid_for(n, 256, p->sm_count), 256, 0, st>>>(p->d_tab, p->d_rowtab, single_view(p, nullptr, d_kept), nullptr, first, n, d_out);
     p->launches++;
     KP_CUDA(cudaGetLastError());
     KP_CUDA(cudaMemcpyAsync(h_out, d_out, n, cudaMemcpyDeviceToHost, st));
@@ -509,6 +532,263 @@ int kp_pattern_counts(kp_plan *p, const int64_t *d_kmerM, const int64_t *d_kmerU
     KP_CUDA(cudaGetLastError());
     KP_CUDA(cudaMemcpyAsync(h_M, d_out, n * 8, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaMemcpyAsync(h_U, d_out + n, n * 8, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ===================================================================================================
+// One DP sharded over the GPUs of a node.  The score table is split by the digit of the top high
+// position; every rank runs the same waves on its own tiles and reads the children that live on a peer straight
+// from the peer's memory (NVLink) inside the DP kernel.  The caller puts a barrier between the waves.
+// ===================================================================================================
+struct kp_shard {
+    kp_plan *plan = nullptr;
+    int rank = 0, world = 1;
+    uint32_t hw_top = 0, radix_top = 0, nslots = 0;
+    uint64_t local_tiles = 0;
+    float *d_best = nullptr;         // this rank's shard (plain cudaMalloc, so that it can be exported over CUDA IPC)
+    uint16_t *d_kept = nullptr;
+    KpView view;
+    uint32_t *d_tiles = nullptr;     // this rank's tiles, wave by wave (global tile numbers, ascending)
+    std::vector<uint64_t> hl_off;    // wave offsets into d_tiles
+    uint32_t *d_counters = nullptr;
+};
+
+// digits of the top position dealt round-robin in order of decreasing level: every rank gets a similar mix of
+// levels (= a similar share of every wave) and a similar number of splits
+static int shard_assignment(const kp_plan *p, int world, uint8_t *owner, uint8_t *slot, uint32_t *nslots_of_rank)
+{
+    const KpTables &t = p->host.t;
+    if (t.nhigh < 1) return fail("sharding needs at least one high position (the pattern is too small to shard)");
+    const int e = t.highpos[t.nhigh - 1];
+    const int radix = t.radix[e];
+    if (world < 1 || world > KP_MAX_SHARDS || world > radix) return fail("sharding: world size must be 1..min(8, radix of the top position)");
+    std::vector<int> digits(radix);
+    for (int d = 0; d < radix; d++) digits[d] = d;
+    auto lvl = [&](int d) { unsigned m = t.digit_mask[e][d]; return (int)((m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + ((m >> 3) & 1)); };
+    std::stable_sort(digits.begin(), digits.end(), [&](int a, int b) { return lvl(a) > lvl(b); });
+    for (int r = 0; r < KP_MAX_SHARDS; r++) nslots_of_rank[r] = 0;
+    memset(owner, 0, 16);
+    memset(slot, 0, 16);
+    for (int i = 0; i < radix; i++) {
+        const int r = i % world, d = digits[i];
+        owner[d] = (uint8_t)r;
+        slot[d] = (uint8_t)nslots_of_rank[r]++;
+    }
+    return 0;
+}
+
+int kp_shard_assignment(const kp_plan *p, int world, uint8_t *owner16, uint8_t *slot16)
+{
+    if (!p || !owner16 || !slot16) return fail("kp_shard_assignment: null argument");
+    uint32_t n[KP_MAX_SHARDS];
+    return shard_assignment(p, world, owner16, slot16, n);
+}
+
+int kp_shard_create(kp_plan *p, int rank, int world, kp_shard **out)
+{
+    if (!p || !out) return fail("kp_shard_create: null argument");
+    const KpTables &t = p->host.t;
+    if (t.r0 != 15) return fail("kp_shard_create: the sharded DP needs an N position in the general pattern");
+    if (rank < 0 || rank >= world) return fail("kp_shard_create: bad rank");
+    KP_CUDA(cudaSetDevice(p->device));
+    kp_shard *s = new kp_shard();
+    uint32_t nslots[KP_MAX_SHARDS];
+    memset(&s->view, 0, sizeof s->view);
+    if (shard_assignment(p, world, s->view.owner, s->view.slot, nslots)) { delete s; return 1; }
+    const int e = t.highpos[t.nhigh - 1];
+    s->plan = p; s->rank = rank; s->world = world;
+    s->hw_top = t.highw[e]; s->radix_top = t.radix[e]; s->nslots = nslots[rank];
+    s->view.hw_top = s->hw_top;
+    s->local_tiles = (uint64_t)s->nslots * s->hw_top;
+    if (s->local_tiles >= (1ull << 28)) { delete s; return fail("kp_shard_create: more than 2^28 tiles per rank"); }
+    // this rank's tiles of every wave, in the order of the plan's tile list
+    const size_t nhl = p->host.hl_off.size() - 1;
+    std::vector<uint32_t> mine;
+    s->hl_off.assign(nhl + 1, 0);
+    for (size_t l = 0; l < nhl; l++) {
+        for (uint64_t i = p->host.hl_off[l]; i < p->host.hl_off[l + 1]; i++) {
+            const uint32_t tile = p->host.tile_order[i];
+            if (s->view.owner[tile / s->hw_top] == rank) mine.push_back(tile);
+        }
+        s->hl_off[l + 1] = mine.size();
+    }
+    if (mine.size() != s->local_tiles) { delete s; return fail("kp_shard_create: internal: tile count"); }
+    cudaError_t e1 = cudaMalloc(&s->d_best, (size_t)s->local_tiles * t.tile_stride * sizeof(float));
+    cudaError_t e2 = cudaMalloc(&s->d_kept, (size_t)s->local_tiles * t.rp * sizeof(uint16_t));
+    cudaError_t e3 = cudaMalloc(&s->d_tiles, sizeof(uint32_t) * (mine.size() + 1));
+    cudaError_t e4 = cudaMalloc(&s->d_counters, sizeof(uint32_t) * 64);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+        cudaFree(s->d_best); cudaFree(s->d_kept); cudaFree(s->d_tiles); cudaFree(s->d_counters);
+        delete s;
+        cudaGetLastError();
+        return fail("kp_shard_create: out of device memory for the shard");
+    }
+    KP_CUDA(cudaMemcpy(s->d_tiles, mine.data(), sizeof(uint32_t) * mine.size(), cudaMemcpyHostToDevice));
+    s->view.best[rank] = s->d_best;
+    s->view.flags[rank] = s->d_kept;
+    for (int wide = 0; wide < 2; wide++)
+        KP_CUDA(cudaFuncSetAttribute(wide ? dp_kernel_sharded<true>(t.rp) : dp_kernel_sharded<false>(t.rp),
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_optin));
+    *out = s;
+    return 0;
+}
+
+int kp_shard_destroy(kp_shard *s)
+{
+    if (!s) return 0;
+    cudaSetDevice(s->plan->device);
+    cudaFree(s->d_best); cudaFree(s->d_kept); cudaFree(s->d_tiles); cudaFree(s->d_counters);
+    delete s;
+    return 0;
+}
+
+int kp_shard_get_info(const kp_shard *s, kp_shard_info *o)
+{
+    if (!s || !o) return fail("kp_shard_get_info: null argument");
+    const KpTables &t = s->plan->host.t;
+    o->local_tiles = s->local_tiles;
+    o->table_elems = s->local_tiles * t.tile_stride;
+    o->kept_elems = s->local_tiles * (uint64_t)t.rp;
+    o->d_best = (uint64_t)(uintptr_t)s->d_best;
+    o->d_kept = (uint64_t)(uintptr_t)s->d_kept;
+    o->rank = (uint32_t)s->rank;
+    o->world = (uint32_t)s->world;
+    o->nwaves = (uint32_t)(s->hl_off.size() - 1);
+    o->top_digits = s->nslots;
+    return 0;
+}
+
+int kp_shard_set_peer(kp_shard *s, int peer, const float *d_best, const uint16_t *d_kept)
+{
+    if (!s || peer < 0 || peer >= s->world || !d_best || !d_kept) return fail("kp_shard_set_peer: bad argument");
+    if (peer == s->rank) return fail("kp_shard_set_peer: peer is this rank");
+    s->view.best[peer] = d_best;
+    s->view.flags[peer] = d_kept;
+    return 0;
+}
+
+// CUDA IPC plumbing for one-process-per-GPU launches: export a device allocation, map a peer's
+int kp_ipc_export(const void *d_ptr, uint8_t *handle64)
+{
+    if (!d_ptr || !handle64) return fail("kp_ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    KP_CUDA(cudaIpcGetMemHandle(&h, (void *)d_ptr));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+int kp_ipc_open(int device, const uint8_t *handle64, void **d_ptr)
+{
+    if (!handle64 || !d_ptr) return fail("kp_ipc_open: null argument");
+    KP_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    KP_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int kp_ipc_close(int device, void *d_ptr)
+{
+    if (!d_ptr) return 0;
+    KP_CUDA(cudaSetDevice(device));
+    KP_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return 0;
+}
+
+int kp_shard_dp_wave(kp_shard *s, int wave, const int64_t *d_expM, const int64_t *d_expU, uint64_t max_count, double alpha,
+                     double beta, double penalty, void *stream)
+{
+    if (!s) return fail("kp_shard_dp_wave: null shard");
+    kp_plan *p = s->plan;
+    const KpTables &t = p->host.t;
+    if (wave < 0 || wave >= (int)s->hl_off.size() - 1 || wave >= 64) return fail("kp_shard_dp_wave: bad wave");
+    for (int r = 0; r < s->world; r++)
+        if (!s->view.best[r] || !s->view.flags[r]) return fail("kp_shard_dp_wave: a peer's shard has not been set");
+    cudaStream_t st = (cudaStream_t)stream;
+    KP_CUDA(cudaSetDevice(p->device));
+    if (wave == 0) KP_CUDA(cudaMemsetAsync(s->d_counters, 0, sizeof(uint32_t) * 64, st));
+    const uint64_t lo = s->hl_off[wave], hi = s->hl_off[wave + 1];
+    if (hi == lo) return 0;
+    const bool wide = max_count > 0xFFFFFFFFull;
+    const int nw = p->nwarps[wide];
+    if (nw < 1) return fail("DP kernel does not fit in shared memory for this tile shape");
+    KpDpParams prm;
+    memset(&prm, 0, sizeof prm);
+    prm.tab = p->d_tab;
+    prm.rowtab = p->d_rowtab;
+    prm.e0 = (const long long *)d_expM;
+    prm.e1 = (const long long *)d_expU;
+    prm.alpha = alpha; prm.beta = beta; prm.penalty = penalty;
+    prm.best = s->d_best;
+    prm.flags = s->d_kept;
+    prm.pf_dist = KP_PF_DIST;
+    prm.view = s->view;
+    prm.my_rank = s->rank;
+    prm.tile_list = s->d_tiles + lo;
+    prm.ntiles_wave = (uint32_t)(hi - lo);
+    prm.counter = s->d_counters + wave;
+    prm.leaf_wave = (wave == 0);
+    const uint64_t ntile = hi - lo;
+    int warps = nw;
+    if (ntile < (uint64_t)p->sm_count * nw) {
+        warps = (int)((ntile + p->sm_count - 1) / p->sm_count);
+        if (warps < 1) warps = 1;
+    }
+    uint64_t grid = (ntile + warps - 1) / warps;
+    if (grid > (uint64_t)p->sm_count) grid = p->sm_count;
+    const size_t sm = 2048 + t.rt_bytes + (size_t)warps * t.warp_smem_bytes[wide];
+    if (t.rp == KP_RP_NN) launch_dp_r0<15, KP_RP_NN, true>(wide, (int)grid, warps * 32, sm, st, prm);
+    else launch_dp_r0<15, 0, true>(wide, (int)grid, warps * 32, sm, st, prm);
+    p->launches++;
+    KP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int kp_shard_backtrack(kp_shard *s, void *d_ws, uint64_t cap, uint64_t root, uint64_t *h_patnums, uint64_t *n_out, void *stream)
+{
+    if (!s || !d_ws || !h_patnums || !n_out) return fail("kp_shard_backtrack: null argument");
+    kp_plan *p = s->plan;
+    if (root == UINT64_MAX) root = p->host.npat - 1;
+    if (root >= p->host.npat) return fail("kp_shard_backtrack: root out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    KP_CUDA(cudaSetDevice(p->device));
+    unsigned long long *sorted, *keys, *ctr;
+    float *vals;
+    if (backtrack_device(p, s->view, d_ws, cap, root, st, &sorted, &keys, &vals, &ctr)) return 1;
+    unsigned long long hc[2] = {0, 0};
+    KP_CUDA(cudaMemcpyAsync(hc, ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    *n_out = hc[0];
+    if (hc[1] || hc[0] > cap) return fail("kp_shard_backtrack: partition larger than the workspace capacity");
+    KP_CUDA(cudaMemcpyAsync(h_patnums, sorted, hc[0] * 8, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// scores / kept-whole flags / split codes of arbitrary patterns, read through the view (any rank's shard)
+int kp_shard_gather(kp_shard *s, const uint64_t *h_patnums, uint64_t n, float *h_best, uint8_t *h_kept, uint8_t *h_codes,
+                    void *stream)
+{
+    if (!s || !h_patnums) return fail("kp_shard_gather: null argument");
+    if (n == 0) return 0;
+    kp_plan *p = s->plan;
+    cudaStream_t st = (cudaStream_t)stream;
+    KP_CUDA(cudaSetDevice(p->device));
+    if (scratch_reserve(p, n * 16, st)) return 1;
+    unsigned long long *d_pat = (unsigned long long *)p->d_scratch;
+    float *d_val = (float *)(d_pat + n);
+    uint8_t *d_k = (uint8_t *)(d_val + n), *d_c = d_k + n;
+    KP_CUDA(cudaMemcpyAsync(d_pat, h_patnums, n * 8, cudaMemcpyHostToDevice, st));
+    const int grid = grid_for(n, 256, p->sm_count);
+    if (h_best) kp_gather_kernel<<<grid, 256, 0, st>>>(p->d_tab, p->d_rowtab, s->view, d_pat, 0, n, d_val);
+    if (h_kept) kp_gather_flags_kernel<<<grid, 256, 0, st>>>(p->d_tab, p->d_rowtab, s->view, d_pat, 0, n, d_k);
+    if (h_codes) kp_split_codes_kernel<<<grid, 256, 0, st>>>(p->d_tab, p->d_rowtab, s->view, d_pat, n, d_c);
+    KP_CUDA(cudaGetLastError());
+    if (h_best) KP_CUDA(cudaMemcpyAsync(h_best, d_val, n * 4, cudaMemcpyDeviceToHost, st));
+    if (h_kept) KP_CUDA(cudaMemcpyAsync(h_kept, d_k, n, cudaMemcpyDeviceToHost, st));
+    if (h_codes) KP_CUDA(cudaMemcpyAsync(h_codes, d_c, n, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaStreamSynchronize(st));
     return 0;
 }

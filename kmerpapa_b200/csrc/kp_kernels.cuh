@@ -161,6 +161,25 @@ __device__ __forceinline__ float2 kp_score_lower_bound2(float2 Mf, float2 Uf, fl
 // ---------------------------------------------------------------------------------------------------
 // K3+K4: lazily fused self-score + min-plus recurrence
 // ---------------------------------------------------------------------------------------------------
+// Where the tiles of a score table live: one table, or one shard per GPU of the node.  A table is
+// sharded by the digit of the TOP high position (the most significant one of the tile number): the tiles of digit d
+// belong to rank owner[d] and are stored there as if the digit were slot[d].  nshard == 1: hw_top = ntiles, so
+// the digit is 0 for every tile and owner[0] = slot[0] = 0.
+#define KP_MAX_SHARDS 8
+struct KpView {
+    const float *best[KP_MAX_SHARDS];        // (peer) pointers to every rank's shard of the score table
+    const uint16_t *flags[KP_MAX_SHARDS];    // ... and of the kept-whole flags
+    uint32_t hw_top;
+    uint8_t owner[16], slot[16];
+};
+
+__device__ __forceinline__ void kp_view_tile(const KpView &v, unsigned long long tile, int &rank, unsigned long long &ltile)
+{
+    const unsigned long long d = tile / v.hw_top;
+    rank = v.owner[d];
+    ltile = (unsigned long long)v.slot[d] * v.hw_top + (tile - d * v.hw_top);
+}
+
 struct KpDpParams {
     const KpTables *tab;
     const uint8_t *rowtab;
@@ -171,13 +190,18 @@ struct KpDpParams {
     int pf_dist;                // L2 prefetch distance of the child-tile stream, in (32 rows x 1 split) steps
     const long long *e0, *e1;   // expanded counts M, U  [ntiles][tile_kmers]
     double alpha, beta, penalty;
-    float *best;                // best loss per pattern
+    float *best;                // best loss per pattern (sharded: this rank's shard)
     uint16_t *flags;            // per row, bit d set = pattern kept whole
+    KpView view;                // sharded DP only: every rank's shard, for the child tiles of the top position
+    int my_rank;
 };
 
 // RP: the row pitch as a compile-time constant (0: read it from the tables).  With the pitch known, the tile
 // stride and the four group offsets of a row fold into immediates of the child-tile loads.
-template <int R0, bool WIDE, int RP>
+// SHARDED: the score table is split over the GPUs of the node by the digit of the top high position; a tile's
+// children along that position may live in a peer's memory and are then loaded over NVLink by the same
+// pipeline (split lists carry the owner rank in their top 4 bits).
+template <int R0, bool WIDE, int RP, bool SHARDED>
 __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const KpDpParams p)
 {
     typedef typename KpCnt<WIDE>::type C;
@@ -223,6 +247,11 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
         it = __shfl_sync(0xffffffffu, it, 0);
         if (it >= p.ntiles_wave) break;
         const uint32_t tile = p.tile_list[it];
+        uint32_t ltile = tile;   // index of the tile in this rank's table
+        if (SHARDED) {
+            const uint32_t dt = tile / p.view.hw_top;
+            ltile = (uint32_t)p.view.slot[dt] * p.view.hw_top + (tile - dt * p.view.hw_top);
+        }
         __syncwarp();  // previous tile's readers of S / bc / hs are done
         // ---- the tile's high-position splits (two child tiles each) ----
         {
@@ -245,8 +274,17 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
             off -= ns;
             for (int j = 0; j < ns; j++) {
                 int c1 = tb.mask_digit[e][tb.ms_c1[m][j]], c2 = tb.mask_digit[e][tb.ms_c2[m][j]];
-                hs1[off + j] = tile - (uint32_t)(d - c1) * hw;
-                hs2[off + j] = tile - (uint32_t)(d - c2) * hw;
+                if (!SHARDED) {
+                    hs1[off + j] = tile - (uint32_t)(d - c1) * hw;
+                    hs2[off + j] = tile - (uint32_t)(d - c2) * hw;
+                } else if (lane == nhigh - 1) {   // top position: d is the sharding digit, tile - d * hw the rest
+                    const uint32_t rest = tile - (uint32_t)d * hw;
+                    hs1[off + j] = ((uint32_t)p.view.slot[c1] * hw + rest) | ((uint32_t)p.view.owner[c1] << 28);
+                    hs2[off + j] = ((uint32_t)p.view.slot[c2] * hw + rest) | ((uint32_t)p.view.owner[c2] << 28);
+                } else {                          // same sharding digit: a local tile
+                    hs1[off + j] = (ltile - (uint32_t)(d - c1) * hw) | ((uint32_t)p.my_rank << 28);
+                    hs2[off + j] = (ltile - (uint32_t)(d - c2) * hw) | ((uint32_t)p.my_rank << 28);
+                }
             }
             if (lane == 0) *s_nhs = total;
         }
@@ -258,7 +296,7 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
         }
         __syncwarp();
         const int nhs = *s_nhs;
-        float4 *otile = (float4 *)(p.best + (size_t)tile * stride);
+        float4 *otile = (float4 *)(p.best + (size_t)ltile * stride);
 
         // ---- phase D: stream the child tiles of the high-position splits for ALL rows of the tile; the running
         //      minimum of row r is parked in S[r] until the row's turn in the schedule.  One flattened software
@@ -275,6 +313,7 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
             const uint32_t stride4 = stride >> 2;                 // tile stride in float4
             int ls = 0, lrow = lane;          // split and row of the next load
             const float4 *lptr = tb4 + (lrow < nrows ? lrow : nrows - 1);   // idle lanes of the last chunk re-read a valid row
+            int lrowc = lrow < nrows ? lrow : nrows - 1;                    // (sharded: the row, the base depends on the owner)
             int us = 0, urow = lane;          // split and row of the next use
             // register-free deepening of the pipeline: every step also asks L2 for the lines of a later step.
             // One prefetch per step: the 2 x NG x 4 lines (128 B = 8 rows) of a step map onto the 32 lanes.
@@ -285,17 +324,29 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
             const bool pf_on = pf_g < NG;
 #define KP_FL_PREFETCH()                                                                              \
     if (pchunk < nrows) {                                                                             \
-        if (pf_on && pchunk + pf_line < nrows)                                                        \
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_ptr + (size_t)pf_hs[ps] * stride4 + pchunk)); \
+        const uint32_t ph_ = pf_hs[ps];                                                               \
+        if (pf_on && pchunk + pf_line < nrows && (!SHARDED || (int)(ph_ >> 28) == p.my_rank))         \
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_ptr + (size_t)(SHARDED ? (ph_ & 0x0fffffffu) : ph_) * stride4 + pchunk)); \
         if (++ps == nhs) { ps = 0; pchunk += 32; }                                                    \
     }
 #define KP_FL_LOAD(xa, xb)                                                                            \
     {                                                                                                 \
         KP_FL_PREFETCH()                                                                              \
-        const float4 *a_ = lptr + (size_t)hs1[ls] * stride4;                                          \
-        const float4 *b_ = lptr + (size_t)hs2[ls] * stride4;                                          \
+        const float4 *a_, *b_;                                                                        \
+        if (!SHARDED) {                                                                               \
+            a_ = lptr + (size_t)hs1[ls] * stride4;                                                    \
+            b_ = lptr + (size_t)hs2[ls] * stride4;                                                    \
+        } else {   /* the child tile may live in a peer's memory: same load, NVLink instead of HBM */  \
+            const uint32_t h1_ = hs1[ls], h2_ = hs2[ls];                                              \
+            a_ = (const float4 *)p.view.best[h1_ >> 28] + lrowc + (size_t)(h1_ & 0x0fffffffu) * stride4; \
+            b_ = (const float4 *)p.view.best[h2_ >> 28] + lrowc + (size_t)(h2_ & 0x0fffffffu) * stride4; \
+        }                                                                                             \
         _Pragma("unroll") for (int g = 0; g < NG; g++) { xa[g] = __ldg(a_ + g * rp); xb[g] = __ldg(b_ + g * rp); } \
-        if (++ls == nhs) { ls = 0; lrow += 32; lptr = tb4 + (lrow < nrows ? lrow : nrows - 1); }      \
+        if (++ls == nhs) {                                                                            \
+            ls = 0; lrow += 32;                                                                       \
+            lrowc = lrow < nrows ? lrow : nrows - 1;                                                  \
+            lptr = tb4 + lrowc;                                                                       \
+        }                                                                                             \
     }
 #define KP_FL_USE(xa, xb)                                                                             \
     {                                                                                                 \
@@ -493,7 +544,7 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
                     S[g * rp + srow] = o;
                     __stcs(otile + g * rp + srow, o);  // next read is a whole wave away: do not keep it in L2
                 }
-                p.flags[(size_t)tile * rp + srow] = (uint16_t)flag;
+                p.flags[(size_t)ltile * rp + srow] = (uint16_t)flag;
             }
             __syncwarp();  // rows of this round visible to the warp
         }
@@ -619,11 +670,28 @@ __device__ __forceinline__ KpLoc kp_locate_dev(const KpTables &tb, const uint16_
     return L;
 }
 
-__device__ __forceinline__ float kp_best_at(const KpTables &tb, const uint16_t *srow_of_row, const float *best,
+// score / kept-whole flag of a located pattern, through the view (any shard)
+__device__ __forceinline__ float kp_view_best(const KpTables &tb, const KpView &vw, unsigned long long tile, uint32_t srow, uint32_t d0)
+{
+    int r;
+    unsigned long long lt;
+    kp_view_tile(vw, tile, r, lt);
+    return vw.best[r][lt * tb.tile_stride + ((size_t)(d0 >> 2) * tb.rp + srow) * 4 + (d0 & 3)];
+}
+
+__device__ __forceinline__ bool kp_view_kept(const KpTables &tb, const KpView &vw, unsigned long long tile, uint32_t srow, uint32_t d0)
+{
+    int r;
+    unsigned long long lt;
+    kp_view_tile(vw, tile, r, lt);
+    return (vw.flags[r][lt * tb.rp + srow] >> d0) & 1u;
+}
+
+__device__ __forceinline__ float kp_best_at(const KpTables &tb, const uint16_t *srow_of_row, const KpView &vw,
                                             unsigned long long pat)
 {
     KpLoc L = kp_locate_dev(tb, srow_of_row, pat);
-    return best[L.tile * tb.tile_stride + ((size_t)(L.d0 >> 2) * tb.rp + L.srow) * 4 + (L.d0 & 3)];
+    return kp_view_best(tb, vw, L.tile, L.srow, L.d0);
 }
 
 // counts of one pattern from an expanded table: sum over the base rows of its row and the bases of its digit
@@ -687,12 +755,11 @@ __global__ void kp_cv_leaf_kernel(const KpTables *tab, const uint8_t *rowtab, co
 
 // The split the reference would have recorded for `pat` (w_numba.py:36-49, :62-64): 0xFF if the pattern is
 // kept whole, else position*8 + j of the first split in scan order whose float32 child sum is the minimum.
-__device__ uint8_t kp_split_code_dev(const KpTables &tb, const uint16_t *srow_of_row, const float *best,
-                                     const uint16_t *flags, unsigned long long pat, unsigned long long *c1_out,
-                                     unsigned long long *c2_out)
+__device__ uint8_t kp_split_code_dev(const KpTables &tb, const uint16_t *srow_of_row, const KpView &vw,
+                                     unsigned long long pat, unsigned long long *c1_out, unsigned long long *c2_out)
 {
     KpLoc L = kp_locate_dev(tb, srow_of_row, pat);
-    if ((flags[L.tile * tb.rp + L.srow] >> L.d0) & 1u) return 0xFF;
+    if (kp_view_kept(tb, vw, L.tile, L.srow, L.d0)) return 0xFF;
     float bv = __int_as_float(0x7f800000);
     uint8_t code = 0xFF;
     for (int e = 0; e < tb.npos; e++) {
@@ -702,7 +769,7 @@ __device__ uint8_t kp_split_code_dev(const KpTables &tb, const uint16_t *srow_of
         for (int j = 0; j < tb.ms_n[m]; j++) {
             int c1 = tb.mask_digit[e][tb.ms_c1[m][j]], c2 = tb.mask_digit[e][tb.ms_c2[m][j]];
             unsigned long long p1 = pat - (unsigned long long)(d - c1) * w, p2 = pat - (unsigned long long)(d - c2) * w;
-            float v = __fadd_rn(kp_best_at(tb, srow_of_row, best, p1), kp_best_at(tb, srow_of_row, best, p2));
+            float v = __fadd_rn(kp_best_at(tb, srow_of_row, vw, p1), kp_best_at(tb, srow_of_row, vw, p2));
             if (v < bv) { bv = v; code = (uint8_t)(tb.pos_id[e] * 8 + j); *c1_out = p1; *c2_out = p2; }
         }
     }
@@ -719,9 +786,9 @@ struct KpBtNode { unsigned long long pat, key; };
 // One launch per depth of the partition tree, one warp per node: lane e evaluates the splits of effective
 // position e (their 2 x nsplit child reads are independent and overlap), then the warp takes the
 // lexicographic minimum of (child sum, scan rank).  ctr: [0] leaves, [1] overflow flag, [2 + d] nodes at depth d.
-__global__ void __launch_bounds__(256) kp_backtrack_level_kernel(const KpTables *tab, const uint8_t *rowtab, const float *best,
-                                                                 const uint16_t *flags, int depth, const KpBtNode *cur,
-                                                                 KpBtNode *nxt, KpBtNode *leaves, unsigned long long cap,
+__global__ void __launch_bounds__(256) kp_backtrack_level_kernel(const KpTables *tab, const uint8_t *rowtab, const KpView vw,
+                                                                 int depth, const KpBtNode *cur, KpBtNode *nxt,
+                                                                 KpBtNode *leaves, unsigned long long cap,
                                                                  unsigned long long *ctr)
 {
     const KpTables &tb = *tab;
@@ -742,14 +809,14 @@ __global__ void __launch_bounds__(256) kp_backtrack_level_kernel(const KpTables 
         }
         KpLoc L;
         L.tile = ntile; L.d0 = nd0; L.srow = srow_of_row[nrow];
-        bool kept = (flags[L.tile * tb.rp + L.srow] >> L.d0) & 1u;
+        bool kept = kp_view_kept(tb, vw, L.tile, L.srow, L.d0);
         auto child_best = [&](int e, int d, int c) -> float {
             unsigned long long ct = ntile;
             uint32_t cr = nrow, cd = nd0;
             if (e == tb.estar) cd = (uint32_t)c;
             else if (tb.is_low[e]) cr -= (uint32_t)(d - c) * tb.roww[e];
             else ct -= (unsigned long long)(d - c) * tb.highw[e];
-            return best[ct * tb.tile_stride + ((size_t)(cd >> 2) * tb.rp + srow_of_row[cr]) * 4 + (cd & 3)];
+            return kp_view_best(tb, vw, ct, srow_of_row[cr], cd);
         };
         float bv = __int_as_float(0x7f800000);
         int code = 0x7fffffff;
@@ -835,7 +902,7 @@ __global__ void kp_backtrack_sort_kernel(const KpBtNode *leaves, const unsigned 
 }
 
 // split codes of arbitrary patterns (test hook and output stage)
-__global__ void kp_split_codes_kernel(const KpTables *tab, const uint8_t *rowtab, const float *best, const uint16_t *flags,
+__global__ void kp_split_codes_kernel(const KpTables *tab, const uint8_t *rowtab, const KpView vw,
                                       const unsigned long long *pats, unsigned long long n, uint8_t *codes)
 {
     const KpTables &tb = *tab;
@@ -843,30 +910,30 @@ __global__ void kp_split_codes_kernel(const KpTables *tab, const uint8_t *rowtab
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         unsigned long long p1, p2;
-        codes[i] = kp_split_code_dev(tb, srow_of_row, best, flags, pats[i], &p1, &p2);
+        codes[i] = kp_split_code_dev(tb, srow_of_row, vw, pats[i], &p1, &p2);
     }
 }
 
 // gather table values of arbitrary patterns: out[i] = table[pattern i]  (also: unpacks whole tables for tests)
-__global__ void kp_gather_kernel(const KpTables *tab, const uint8_t *rowtab, const float *table,
+__global__ void kp_gather_kernel(const KpTables *tab, const uint8_t *rowtab, const KpView vw,
                                  const unsigned long long *pats, unsigned long long first, unsigned long long n, float *out)
 {
     const KpTables &tb = *tab;
     const uint16_t *srow_of_row = (const uint16_t *)(rowtab + tb.rt_srow_of_row);
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * blockDim.x)
-        out[i] = kp_best_at(tb, srow_of_row, table, pats ? pats[i] : first + i);
+        out[i] = kp_best_at(tb, srow_of_row, vw, pats ? pats[i] : first + i);
 }
 
-__global__ void kp_gather_flags_kernel(const KpTables *tab, const uint8_t *rowtab, const uint16_t *flags,
-                                       unsigned long long first, unsigned long long n, uint8_t *out)
+__global__ void kp_gather_flags_kernel(const KpTables *tab, const uint8_t *rowtab, const KpView vw,
+                                       const unsigned long long *pats, unsigned long long first, unsigned long long n, uint8_t *out)
 {
     const KpTables &tb = *tab;
     const uint16_t *srow_of_row = (const uint16_t *)(rowtab + tb.rt_srow_of_row);
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * blockDim.x) {
-        KpLoc L = kp_locate_dev(tb, srow_of_row, first + i);
-        out[i] = (uint8_t)((flags[L.tile * tb.rp + L.srow] >> L.d0) & 1u);
+        KpLoc L = kp_locate_dev(tb, srow_of_row, pats ? pats[i] : first + i);
+        out[i] = (uint8_t)kp_view_kept(tb, vw, L.tile, L.srow, L.d0);
     }
 }
 

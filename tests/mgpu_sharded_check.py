@@ -1,0 +1,84 @@
+"""Run under torchrun on N GPUs: one DP sharded over the ranks (CUDA IPC peer pointers, NCCL barrier between waves)
+must give the partition, the top score and the split codes of the unsharded DP computed on rank 0.
+Usage: torchrun --nproc-per-node N tests/mgpu_sharded_check.py [gen_pat] [reps]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from kmerpapa_b200 import sharded, synthetic
+from kmerpapa_b200.engine import get_plan
+
+
+def main():
+    gen_pat = sys.argv[1] if len(sys.argv) > 1 else "NNNNANNN"
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    kmers, pos, neg = synthetic.negbin_counts(gen_pat, 4242)
+    plan = get_plan(gen_pat, local)
+    kM, kU = plan.pack_counts(synthetic.codes_of(kmers), pos, neg)
+    eM, eU = plan.expand(kM, kU)
+    mc = int(pos.sum() + neg.sum())
+    mu = int(pos.sum()) / mc
+    alpha, penalty = 1.0, 6.0
+    beta = alpha * (1 - mu) / mu
+    sh = sharded.ShardedDP(plan, rank, world)
+    sh.connect()
+    ms = []
+    for rep in range(reps):
+        sh.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sh.run(eM, eU, mc, alpha, beta, penalty)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=plan.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms.append(float(t.item()))
+    part = sh.backtrack()
+    top = sh.top_score()
+    rng = np.random.default_rng(11)
+    pats = np.unique(np.concatenate([rng.integers(0, plan.npat, size=50000, dtype=np.uint64), part]))
+    vals, flags, codes = sh.gather(pats, codes=True)
+    ok = True
+    if rank == 0:
+        fits = plan.info.table_elems * 4 < 150e9
+        if fits:
+            best, kept = plan.dp_single(eM, eU, mc, alpha, beta, penalty)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            best, kept = plan.dp_single(eM, eU, mc, alpha, beta, penalty)
+            e1.record()
+            torch.cuda.synchronize()
+            single_ms = e0.elapsed_time(e1)
+            ref_part = plan.backtrack(best, kept)
+            ref_codes = plan.split_codes(best, kept, pats)
+            ok = (np.array_equal(part, ref_part) and plan.top_score(best) == top and np.array_equal(codes, ref_codes))
+            print(f"{gen_pat}: npat {plan.npat}, world {world}: sharded {min(ms):.3f} ms ({plan.npat / min(ms) / 1e6:.1f} Gpat/s), "
+                  f"one GPU {single_ms:.3f} ms, speed-up {single_ms / min(ms):.2f}x, partition {len(part)} patterns, "
+                  f"top {top}", flush=True)
+        else:
+            print(f"{gen_pat}: npat {plan.npat}, world {world}: sharded {min(ms):.3f} ms ({plan.npat / min(ms) / 1e6:.1f} Gpat/s), "
+                  f"partition {len(part)} patterns, top {top} (too large for one GPU: no unsharded comparison)", flush=True)
+    # every rank must see the same results through its own peer mappings
+    blob = [None] * world
+    dist.all_gather_object(blob, (float(top), part.tobytes(), codes.tobytes()))
+    ok = ok and all(b == blob[0] for b in blob)
+    flag = torch.tensor([1 if ok else 0], device=plan.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("SHARDED OK" if int(flag.item()) == 1 else "SHARDED MISMATCH", flush=True)
+    sh.close()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
