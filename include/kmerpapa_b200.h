@@ -174,12 +174,17 @@ typedef struct kp_shard_info {
     uint32_t rank, world;
     uint32_t nwaves;        /* waves of the DP (the same on every rank) */
     uint32_t top_digits;    /* digits of the top high position owned by this rank */
+    uint32_t replicate;     /* 1: replicated mode */
+    uint32_t reserved;
 } kp_shard_info;
 
 /* owner rank and local slot of every digit of the top high position (16 entries each) for `world` ranks */
 int kp_shard_assignment(const kp_plan *plan, int world, uint8_t *owner16, uint8_t *slot16);
-/* allocate this rank's shard on the plan's device; world <= min(8, radix of the top position); needs an N position */
-int kp_shard_create(kp_plan *plan, int rank, int world, kp_shard **out);
+/* allocate this rank's shard on the plan's device; world <= min(8, radix of the top position); needs an N position.
+ * replicate = 0 (capacity): a rank stores only its own tiles and the kernel LOADS peer children over NVLink;
+ * replicate = 1 (speed): every rank allocates a full-size table, the kernel reads locally and PUSHES each finished
+ *   row into the table of every peer that owns a superset digit (posted NVLink writes). */
+int kp_shard_create(kp_plan *plan, int rank, int world, int replicate, kp_shard **out);
 int kp_shard_destroy(kp_shard *shard);
 int kp_shard_get_info(const kp_shard *shard, kp_shard_info *out);
 /* device pointers (valid on this rank's device: peer-mapped) of rank `peer`'s shard */

@@ -28,6 +28,7 @@ class ShardInfo(ctypes.Structure):
         ("local_tiles", ctypes.c_uint64), ("table_elems", ctypes.c_uint64), ("kept_elems", ctypes.c_uint64),
         ("d_best", ctypes.c_uint64), ("d_kept", ctypes.c_uint64),
         ("rank", ctypes.c_uint32), ("world", ctypes.c_uint32), ("nwaves", ctypes.c_uint32), ("top_digits", ctypes.c_uint32),
+        ("replicate", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
     ]
 
 
@@ -54,7 +55,7 @@ SYMBOLS = {
     "kp_pattern_offset": (_int, [_vp, _u64, ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(ctypes.c_uint32)]),
     "kp_plan_launch_count": (_u64, [_vp]),
     "kp_shard_assignment": (_int, [_vp, _int, _vp, _vp]),
-    "kp_shard_create": (_int, [_vp, _int, _int, ctypes.POINTER(_vp)]),
+    "kp_shard_create": (_int, [_vp, _int, _int, _int, ctypes.POINTER(_vp)]),
     "kp_shard_destroy": (_int, [_vp]),
     "kp_shard_get_info": (_int, [_vp, ctypes.POINTER(ShardInfo)]),
     "kp_shard_set_peer": (_int, [_vp, _int, _vp, _vp]),

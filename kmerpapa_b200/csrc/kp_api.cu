@@ -56,28 +56,28 @@ template <bool WIDE>
 static const void *dp_kernel_for_radix(int r0, int rp)
 {
     switch (r0) {
-    case 1: return (const void *)kp_dp_rows_kernel<1, WIDE, 0, false>;
-    case 3: return (const void *)kp_dp_rows_kernel<3, WIDE, 0, false>;
-    case 7: return (const void *)kp_dp_rows_kernel<7, WIDE, 0, false>;
+    case 1: return (const void *)kp_dp_rows_kernel<1, WIDE, 0, 0>;
+    case 3: return (const void *)kp_dp_rows_kernel<3, WIDE, 0, 0>;
+    case 7: return (const void *)kp_dp_rows_kernel<7, WIDE, 0, 0>;
     default:
-        return rp == KP_RP_NN ? (const void *)kp_dp_rows_kernel<15, WIDE, KP_RP_NN, false>
-                              : (const void *)kp_dp_rows_kernel<15, WIDE, 0, false>;
+        return rp == KP_RP_NN ? (const void *)kp_dp_rows_kernel<15, WIDE, KP_RP_NN, 0>
+                              : (const void *)kp_dp_rows_kernel<15, WIDE, 0, 0>;
     }
 }
 
-template <int R0, int RP, bool SHARDED>
+template <int R0, int RP, int SHARD>
 static void launch_dp_r0(bool wide, int grid, int threads, size_t smem, cudaStream_t st, const KpDpParams &prm)
 {
-    if (wide) kp_dp_rows_kernel<R0, true, RP, SHARDED><<<grid, threads, smem, st>>>(prm);
-    else kp_dp_rows_kernel<R0, false, RP, SHARDED><<<grid, threads, smem, st>>>(prm);
+    if (wide) kp_dp_rows_kernel<R0, true, RP, SHARD><<<grid, threads, smem, st>>>(prm);
+    else kp_dp_rows_kernel<R0, false, RP, SHARD><<<grid, threads, smem, st>>>(prm);
 }
 
 // the sharded DP exists for the register radix 15 only (a pattern without an N position is far too small to shard)
-template <bool WIDE>
+template <bool WIDE, int SHARD>
 static const void *dp_kernel_sharded(int rp)
 {
-    return rp == KP_RP_NN ? (const void *)kp_dp_rows_kernel<15, WIDE, KP_RP_NN, true>
-                          : (const void *)kp_dp_rows_kernel<15, WIDE, 0, true>;
+    return rp == KP_RP_NN ? (const void *)kp_dp_rows_kernel<15, WIDE, KP_RP_NN, SHARD>
+                          : (const void *)kp_dp_rows_kernel<15, WIDE, 0, SHARD>;
 }
 
 // a view of one unsharded table
@@ -322,12 +322,12 @@ static int launch_dp(kp_plan *p, bool wide, KpDpParams prm, cudaStream_t st)
         if (grid > (uint64_t)p->sm_count) grid = p->sm_count;
         size_t sm = 2048 + t.rt_bytes + (size_t)warps * t.warp_smem_bytes[wide];
         switch (t.r0) {
-        case 1: launch_dp_r0<1, 0, false>(wide, (int)grid, warps * 32, sm, st, prm); break;
-        case 3: launch_dp_r0<3, 0, false>(wide, (int)grid, warps * 32, sm, st, prm); break;
-        case 7: launch_dp_r0<7, 0, false>(wide, (int)grid, warps * 32, sm, st, prm); break;
+        case 1: launch_dp_r0<1, 0, 0>(wide, (int)grid, warps * 32, sm, st, prm); break;
+        case 3: launch_dp_r0<3, 0, 0>(wide, (int)grid, warps * 32, sm, st, prm); break;
+        case 7: launch_dp_r0<7, 0, 0>(wide, (int)grid, warps * 32, sm, st, prm); break;
         default:
-            if (t.rp == KP_RP_NN) launch_dp_r0<15, KP_RP_NN, false>(wide, (int)grid, warps * 32, sm, st, prm);
-            else launch_dp_r0<15, 0, false>(wide, (int)grid, warps * 32, sm, st, prm);
+            if (t.rp == KP_RP_NN) launch_dp_r0<15, KP_RP_NN, 0>(wide, (int)grid, warps * 32, sm, st, prm);
+            else launch_dp_r0<15, 0, 0>(wide, (int)grid, warps * 32, sm, st, prm);
             break;
         }
         p->launches++;
@@ -544,6 +544,7 @@ int kp_pattern_counts(kp_plan *p, const int64_t *d_kmerM, const int64_t *d_kmerU
 struct kp_shard {
     kp_plan *plan = nullptr;
     int rank = 0, world = 1;
+    bool replicate = false;          // every rank holds a full-size table and finished tiles are pushed to their readers
     uint32_t hw_top = 0, radix_top = 0, nslots = 0;
     uint64_t local_tiles = 0;
     float *d_best = nullptr;         // this rank's shard (plain cudaMalloc, so that it can be exported over CUDA IPC)
@@ -585,7 +586,7 @@ int kp_shard_assignment(const kp_plan *p, int world, uint8_t *owner16, uint8_t *
     return shard_assignment(p, world, owner16, slot16, n);
 }
 
-int kp_shard_create(kp_plan *p, int rank, int world, kp_shard **out)
+int kp_shard_create(kp_plan *p, int rank, int world, int replicate, kp_shard **out)
 {
     if (!p || !out) return fail("kp_shard_create: null argument");
     const KpTables &t = p->host.t;
@@ -597,10 +598,23 @@ int kp_shard_create(kp_plan *p, int rank, int world, kp_shard **out)
     memset(&s->view, 0, sizeof s->view);
     if (shard_assignment(p, world, s->view.owner, s->view.slot, nslots)) { delete s; return 1; }
     const int e = t.highpos[t.nhigh - 1];
-    s->plan = p; s->rank = rank; s->world = world;
+    s->plan = p; s->rank = rank; s->world = world; s->replicate = replicate != 0;
     s->hw_top = t.highw[e]; s->radix_top = t.radix[e]; s->nslots = nslots[rank];
     s->view.hw_top = s->hw_top;
-    s->local_tiles = (uint64_t)s->nslots * s->hw_top;
+    const uint64_t own_tiles = (uint64_t)s->nslots * s->hw_top;
+    s->local_tiles = own_tiles;
+    if (s->replicate) {   // full-size table, global tile numbers; readers of a digit = owners of its strict supersets
+        s->local_tiles = t.ntiles;
+        for (int d = 0; d < (int)s->radix_top; d++) {
+            s->view.slot[d] = (uint8_t)d;
+            unsigned mask = 0;
+            for (int q = 0; q < (int)s->radix_top; q++) {
+                const unsigned md = t.digit_mask[e][d], mq = t.digit_mask[e][q];
+                if (q != d && (md & mq) == md && s->view.owner[q] != s->view.owner[d]) mask |= 1u << s->view.owner[q];
+            }
+            s->view.push_mask[d] = (uint8_t)mask;
+        }
+    }
     if (s->local_tiles >= (1ull << 28)) { delete s; return fail("kp_shard_create: more than 2^28 tiles per rank"); }
     // this rank's tiles of every wave, in the order of the plan's tile list
     const size_t nhl = p->host.hl_off.size() - 1;
@@ -613,7 +627,7 @@ int kp_shard_create(kp_plan *p, int rank, int world, kp_shard **out)
         }
         s->hl_off[l + 1] = mine.size();
     }
-    if (mine.size() != s->local_tiles) { delete s; return fail("kp_shard_create: internal: tile count"); }
+    if (mine.size() != own_tiles) { delete s; return fail("kp_shard_create: internal: tile count"); }
     cudaError_t e1 = cudaMalloc(&s->d_best, (size_t)s->local_tiles * t.tile_stride * sizeof(float));
     cudaError_t e2 = cudaMalloc(&s->d_kept, (size_t)s->local_tiles * t.rp * sizeof(uint16_t));
     cudaError_t e3 = cudaMalloc(&s->d_tiles, sizeof(uint32_t) * (mine.size() + 1));
@@ -627,9 +641,10 @@ int kp_shard_create(kp_plan *p, int rank, int world, kp_shard **out)
     KP_CUDA(cudaMemcpy(s->d_tiles, mine.data(), sizeof(uint32_t) * mine.size(), cudaMemcpyHostToDevice));
     s->view.best[rank] = s->d_best;
     s->view.flags[rank] = s->d_kept;
-    for (int wide = 0; wide < 2; wide++)
-        KP_CUDA(cudaFuncSetAttribute(wide ? dp_kernel_sharded<true>(t.rp) : dp_kernel_sharded<false>(t.rp),
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_optin));
+    KP_CUDA(cudaFuncSetAttribute(dp_kernel_sharded<true, 1>(t.rp), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_optin));
+    KP_CUDA(cudaFuncSetAttribute(dp_kernel_sharded<false, 1>(t.rp), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_optin));
+    KP_CUDA(cudaFuncSetAttribute(dp_kernel_sharded<true, 2>(t.rp), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_optin));
+    KP_CUDA(cudaFuncSetAttribute(dp_kernel_sharded<false, 2>(t.rp), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_optin));
     *out = s;
     return 0;
 }
@@ -656,6 +671,7 @@ int kp_shard_get_info(const kp_shard *s, kp_shard_info *o)
     o->world = (uint32_t)s->world;
     o->nwaves = (uint32_t)(s->hl_off.size() - 1);
     o->top_digits = s->nslots;
+    o->replicate = s->replicate ? 1u : 0u;
     return 0;
 }
 
@@ -739,8 +755,13 @@ int kp_shard_dp_wave(kp_shard *s, int wave, const int64_t *d_expM, const int64_t
     uint64_t grid = (ntile + warps - 1) / warps;
     if (grid > (uint64_t)p->sm_count) grid = p->sm_count;
     const size_t sm = 2048 + t.rt_bytes + (size_t)warps * t.warp_smem_bytes[wide];
-    if (t.rp == KP_RP_NN) launch_dp_r0<15, KP_RP_NN, true>(wide, (int)grid, warps * 32, sm, st, prm);
-    else launch_dp_r0<15, 0, true>(wide, (int)grid, warps * 32, sm, st, prm);
+    if (s->replicate) {
+        if (t.rp == KP_RP_NN) launch_dp_r0<15, KP_RP_NN, 2>(wide, (int)grid, warps * 32, sm, st, prm);
+        else launch_dp_r0<15, 0, 2>(wide, (int)grid, warps * 32, sm, st, prm);
+    } else {
+        if (t.rp == KP_RP_NN) launch_dp_r0<15, KP_RP_NN, 1>(wide, (int)grid, warps * 32, sm, st, prm);
+        else launch_dp_r0<15, 0, 1>(wide, (int)grid, warps * 32, sm, st, prm);
+    }
     p->launches++;
     KP_CUDA(cudaGetLastError());
     return 0;

@@ -171,6 +171,7 @@ struct KpView {
     const uint16_t *flags[KP_MAX_SHARDS];    // ... and of the kept-whole flags
     uint32_t hw_top;
     uint8_t owner[16], slot[16];
+    uint8_t push_mask[16];   // replicated mode: ranks (bit r) that own a strict superset of the digit, i.e. read its tiles
 };
 
 __device__ __forceinline__ void kp_view_tile(const KpView &v, unsigned long long tile, int &rank, unsigned long long &ltile)
@@ -198,15 +199,19 @@ struct KpDpParams {
 
 // RP: the row pitch as a compile-time constant (0: read it from the tables).  With the pitch known, the tile
 // stride and the four group offsets of a row fold into immediates of the child-tile loads.
-// SHARDED: the score table is split over the GPUs of the node by the digit of the top high position; a tile's
-// children along that position may live in a peer's memory and are then loaded over NVLink by the same
-// pipeline (split lists carry the owner rank in their top 4 bits).
-template <int R0, bool WIDE, int RP, bool SHARDED>
+// SHARD: the tiles are split over the GPUs of the node by the digit of the top high position.
+//   1 (partitioned, capacity): every rank stores its own tiles only; a tile's children along the top position may
+//     live in a peer's memory and are then loaded over NVLink by the same pipeline (split lists carry the owner
+//     rank in their top 4 bits).
+//   2 (replicated, speed): every rank holds a full-size table; a finished row is stored locally AND into the
+//     table of every peer that owns a superset digit (posted NVLink writes), so all reads stay local.
+template <int R0, bool WIDE, int RP, int SHARD>
 __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const KpDpParams p)
 {
     typedef typename KpCnt<WIDE>::type C;
     constexpr int NG = (R0 + 3) / 4;
     constexpr int NB = R0 == 15 ? 4 : (R0 == 7 ? 3 : (R0 == 3 ? 2 : 1));
+    constexpr bool SHARDED = SHARD == 1;   // partitioned addressing
 
     extern __shared__ __align__(16) unsigned char smem[];
     const KpTables &tb = *p.tab;
@@ -297,6 +302,8 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
         __syncwarp();
         const int nhs = *s_nhs;
         float4 *otile = (float4 *)(p.best + (size_t)ltile * stride);
+        uint32_t pushm = 0;   // replicated mode: peers that will read this tile
+        if (SHARD == 2) pushm = p.view.push_mask[tile / p.view.hw_top];
 
         // ---- phase D: stream the child tiles of the high-position splits for ALL rows of the tile; the running
         //      minimum of row r is parked in S[r] until the row's turn in the schedule.  One flattened software
@@ -545,6 +552,16 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
                     __stcs(otile + g * rp + srow, o);  // next read is a whole wave away: do not keep it in L2
                 }
                 p.flags[(size_t)ltile * rp + srow] = (uint16_t)flag;
+                if (SHARD == 2) {
+                    for (uint32_t pm = pushm; pm; pm &= pm - 1) {   // posted writes into the peers' replicas
+                        const int r = __ffs(pm) - 1;
+                        float4 *rt_ = (float4 *)(const_cast<float *>(p.view.best[r]) + (size_t)tile * stride);
+#pragma unroll
+                        for (int g = 0; g < NG; g++)
+                            rt_[g * rp + srow] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                        const_cast<uint16_t *>(p.view.flags[r])[(size_t)tile * rp + srow] = (uint16_t)flag;
+                    }
+                }
             }
             __syncwarp();  // rows of this round visible to the warp
         }

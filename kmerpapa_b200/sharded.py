@@ -31,11 +31,15 @@ def assignment(plan, world):
 class ShardedDP:
     """This rank's shard of one DP.  `plan` is the PartitionPlan of the general pattern on this rank's device."""
 
-    def __init__(self, plan, rank, world):
+    def __init__(self, plan, rank, world, replicate=False):
+        """replicate=False (capacity mode): a rank stores its own tiles only, the kernel loads peer children over
+        NVLink.  replicate=True (speed mode): every rank holds a full-size table and the kernel pushes finished
+        rows to the peers that will read them, so every read is local."""
         self.plan, self.lib = plan, plan.lib
         self.rank, self.world = int(rank), int(world)
         h = ctypes.c_void_p()
-        check(self.lib.kp_shard_create(plan.handle, self.rank, self.world, ctypes.byref(h)), "kp_shard_create")
+        check(self.lib.kp_shard_create(plan.handle, self.rank, self.world, 1 if replicate else 0, ctypes.byref(h)),
+              "kp_shard_create")
         self.handle = h
         info = _native.ShardInfo()
         check(self.lib.kp_shard_get_info(h, ctypes.byref(info)), "kp_shard_get_info")

@@ -1,6 +1,6 @@
 """Run under torchrun on N GPUs: one DP sharded over the ranks (CUDA IPC peer pointers, NCCL barrier between waves)
 must give the partition, the top score and the split codes of the unsharded DP computed on rank 0.
-Usage: torchrun --nproc-per-node N tests/mgpu_sharded_check.py [gen_pat] [reps]"""
+Usage: torchrun --nproc-per-node N tests/mgpu_sharded_check.py [gen_pat] [reps] [replicate 0|1]"""
 import os
 import sys
 
@@ -16,6 +16,7 @@ from kmerpapa_b200.engine import get_plan
 def main():
     gen_pat = sys.argv[1] if len(sys.argv) > 1 else "NNNNANNN"
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    replicate = bool(int(sys.argv[3])) if len(sys.argv) > 3 else False
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -27,7 +28,7 @@ def main():
     mu = int(pos.sum()) / mc
     alpha, penalty = 1.0, 6.0
     beta = alpha * (1 - mu) / mu
-    sh = sharded.ShardedDP(plan, rank, world)
+    sh = sharded.ShardedDP(plan, rank, world, replicate=replicate)
     sh.connect()
     ms = []
     for rep in range(reps):
@@ -61,7 +62,7 @@ def main():
             ref_part = plan.backtrack(best, kept)
             ref_codes = plan.split_codes(best, kept, pats)
             ok = (np.array_equal(part, ref_part) and plan.top_score(best) == top and np.array_equal(codes, ref_codes))
-            print(f"{gen_pat}: npat {plan.npat}, world {world}: sharded {min(ms):.3f} ms ({plan.npat / min(ms) / 1e6:.1f} Gpat/s), "
+            print(f"{gen_pat}: npat {plan.npat}, world {world}, {'replicated' if replicate else 'partitioned'}: sharded {min(ms):.3f} ms ({plan.npat / min(ms) / 1e6:.1f} Gpat/s), "
                   f"one GPU {single_ms:.3f} ms, speed-up {single_ms / min(ms):.2f}x, partition {len(part)} patterns, "
                   f"top {top}", flush=True)
         else:

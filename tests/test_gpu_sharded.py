@@ -25,9 +25,10 @@ def _setup(gen_pat, seed):
     return plan, eM, eU, mc, 1.0 * (1 - mu) / mu
 
 
+@pytest.mark.parametrize("replicate", [False, True])
 @pytest.mark.parametrize("gen_pat,world", [("NNNNANN", 1), ("NNNNANN", 2), ("NNNNANN", 3), ("NNNNANN", 8),
                                            ("NNNNM", 2), ("NNNNM", 3), ("NNNNTNB", 4)])
-def test_sharded_equals_unsharded(gen_pat, world):
+def test_sharded_equals_unsharded(gen_pat, world, replicate):
     import torch
 
     from kmerpapa_b200 import sharded
@@ -43,10 +44,10 @@ def test_sharded_equals_unsharded(gen_pat, world):
     ref_vals = np.array([plan.gather(best, int(p), 1)[0] for p in pats[:50]], dtype=np.float32)
     top = plan.top_score(best)
 
-    shards = [sharded.ShardedDP(plan, r, world) for r in range(world)]
+    shards = [sharded.ShardedDP(plan, r, world, replicate=replicate) for r in range(world)]
     try:
         owner, slot = sharded.assignment(plan, world)
-        assert sum(s.info.local_tiles for s in shards) == plan.info.ntiles
+        assert sum(s.info.local_tiles for s in shards) == plan.info.ntiles * (world if replicate else 1)
         assert max(s.info.top_digits for s in shards) - min(s.info.top_digits for s in shards) <= 1
         for s in shards:
             s.connect_local(shards)
