@@ -44,11 +44,28 @@ def main():
         ms.append(float(t.item()))
     part = sh.backtrack()
     top = sh.top_score()
+    # size-independent properties of the result (the only checks available when the table exceeds one GPU):
+    # the partition covers every k-mer exactly once, its counts add up to the totals, and the loss of the
+    # general pattern is the sum of the leaves' self-scores (float32 tree sum vs float64 here: 1e-5 relative)
+    from kmerpapa_b200 import iupac
+
+    PE = iupac.PatternEnumeration(gen_pat)
+    names = [PE.num2pattern(int(x)) for x in part]
+    nk = sum(int(np.prod([len(iupac.matches(c)) for c in nm])) for nm in names)
+    M, U = plan.pattern_counts(kM, kU, part)
+    prop = (nk == len(kmers) and int(M.sum()) == int(pos.sum()) and int(U.sum()) == int(neg.sum()))
+    Md, Ud = M.astype(np.float64), U.astype(np.float64)
+    pr = (Md + alpha) / (Md + Ud + alpha + beta)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        leaf = penalty - 2.0 * (np.where(M > 0, Md * np.log(pr), 0.0) + np.where(U > 0, Ud * np.log1p(-pr), 0.0))
+    prop = prop and abs(float(leaf.sum()) - float(top)) <= 1e-5 * abs(float(top))
     rng = np.random.default_rng(11)
     pats = np.unique(np.concatenate([rng.integers(0, plan.npat, size=50000, dtype=np.uint64), part]))
     vals, flags, codes = sh.gather(pats, codes=True)
-    ok = True
+    ok = bool(prop)
     if rank == 0:
+        print(f"properties: k-mers covered {nk}/{len(kmers)}, counts {int(M.sum())}/{int(pos.sum())} {int(U.sum())}/{int(neg.sum())}, "
+              f"sum of leaf scores {leaf.sum():.1f} vs top {float(top):.1f} -> {'ok' if prop else 'FAIL'}", flush=True)
         fits = plan.info.table_elems * 4 < 150e9
         if fits:
             best, kept = plan.dp_single(eM, eU, mc, alpha, beta, penalty)
@@ -61,7 +78,7 @@ def main():
             single_ms = e0.elapsed_time(e1)
             ref_part = plan.backtrack(best, kept)
             ref_codes = plan.split_codes(best, kept, pats)
-            ok = (np.array_equal(part, ref_part) and plan.top_score(best) == top and np.array_equal(codes, ref_codes))
+            ok = ok and (np.array_equal(part, ref_part) and plan.top_score(best) == top and np.array_equal(codes, ref_codes))
             print(f"{gen_pat}: npat {plan.npat}, world {world}, {'replicated' if replicate else 'partitioned'}: sharded {min(ms):.3f} ms ({plan.npat / min(ms) / 1e6:.1f} Gpat/s), "
                   f"one GPU {single_ms:.3f} ms, speed-up {single_ms / min(ms):.2f}x, partition {len(part)} patterns, "
                   f"top {top}", flush=True)
