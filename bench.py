@@ -335,6 +335,46 @@ def bench_cv(args, rank, world, local, steps=None, warmup=None):
     return out
 
 
+def bench_sharded_dp(rank, world, local, reps=6):
+    """Secondary N>1 measurement: ONE 9-mer DP (config 3) sharded over the ranks (kmerpapa_b200/sharded.py, replicated
+    mode: rows pushed to their readers over NVLink inside the DP kernel).  Device time, max over ranks, best of reps."""
+    import torch
+    import torch.distributed as dist
+
+    from kmerpapa_b200 import sharded, synthetic
+    from kmerpapa_b200.engine import get_plan
+
+    kmers, pos, neg = synthetic.negbin_counts(GEN_PAT, 9003)
+    plan = get_plan(GEN_PAT, local)
+    kM, kU = plan.pack_counts(synthetic.codes_of(kmers), pos, neg)
+    eM, eU = plan.expand(kM, kU)
+    mc = int(pos.sum() + neg.sum())
+    mu = int(pos.sum()) / mc
+    alpha, penalty = 1.0, 6.0
+    beta = alpha * (1.0 - mu) / mu
+    sh = sharded.ShardedDP(plan, rank, world, replicate=True)
+    sh.connect()
+    ms = []
+    for _ in range(reps):
+        sh.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sh.run(eM, eU, mc, alpha, beta, penalty)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=plan.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms.append(float(t.item()))
+    part = sh.backtrack()
+    top = float(sh.top_score())
+    sh.close()
+    best = min(ms[1:])
+    return {"workload": "cfg3 single 9-mer DP sharded by the top high digit, replicated mode", "ms": best,
+            "pattern_scores_per_s": plan.npat / (best / 1e3), "partition_patterns": int(len(part)), "loss": top,
+            "reps_ms": [round(x, 3) for x in ms]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -343,6 +383,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cv", action="store_true", help="N=1: skip the secondary CV-grid measurement")
+    ap.add_argument("--no-sharded", action="store_true", help="N>1: skip the secondary sharded single-DP measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -376,6 +417,8 @@ def main():
                     "note": "each step packs the host fold tables (H2D) and reads every job's losses back (D2H)"},
             "cv_grid": cvres, "gpu_launches": cvres["launches"], "clocks": cvres["clocks"],
         }
+        if not args.no_sharded and world <= 8:
+            line["sharded_single_dp"] = bench_sharded_dp(rank, world, local)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_sample_run()
         line["cpu_baseline"] = {
