@@ -107,6 +107,8 @@ def dist_setup(ngpus):
     if world > 1:
         import torch.distributed as dist
 
+        # NCCL writes its banner / debug lines to stdout; stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
