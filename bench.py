@@ -107,8 +107,6 @@ def dist_setup(ngpus):
     if world > 1:
         import torch.distributed as dist
 
-        # NCCL writes its banner / debug lines to stdout; stdout carries exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
@@ -167,7 +165,7 @@ def cpu_sample_run(nthreads=0):
     return {"npat": npat, "seconds": dt, "threads": threads, "partition": n}
 
 
-def run_reference(args):
+def run_reference(args, emit):
     """--impl reference: the reference's CPU path (oracle port, all host threads) on the bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -191,7 +189,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "patterns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -387,8 +385,17 @@ def main():
     ap.add_argument("--no-cv", action="store_true", help="N=1: skip the secondary CV-grid measurement")
     ap.add_argument("--no-sharded", action="store_true", help="N>1: skip the secondary sharded single-DP measurement")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: everything else that writes to file descriptor 1 (the NCCL banner,
+    # stray prints of libraries) is sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, emit)
         return
     import __graft_entry__ as ge
 
@@ -433,7 +440,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
 
 
 if __name__ == "__main__":
