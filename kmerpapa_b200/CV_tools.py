@@ -24,6 +24,30 @@ def draw_multivariate_hypergeometric(m, colors, prng):
     return picked
 
 
+def iter_fold_counts(kmers, pos, neg, nfolds, prng, itype=np.uint64):
+    """The same sampler as sample_fold_counts, one fold at a time: yields (f, M, U) with the held-out counts of
+    fold f in the order of `kmers`.  Fold f is final as soon as it has been drawn, so a consumer can start the
+    jobs of fold f while fold f + 1 is still being drawn."""
+    n = len(kmers)
+    order = sorted(range(n), key=kmers.__getitem__)
+    inv = np.asarray(order)
+    urn = np.empty(2 * n, dtype=itype)
+    urn[:n] = np.asarray(pos, dtype=itype)[inv]
+    urn[n:] = np.asarray(neg, dtype=itype)[inv]
+    per_fold = urn.sum() // nfolds
+    for f in range(nfolds):
+        if f < nfolds - 1:
+            got = draw_multivariate_hypergeometric(per_fold, urn, prng)
+            urn -= got
+        else:
+            got = urn
+        M = np.empty(n, dtype=itype)
+        U = np.empty(n, dtype=itype)
+        M[inv] = got[:n]
+        U[inv] = got[n:]
+        yield f, M, U
+
+
 def sample_fold_counts(kmers, pos, neg, nfolds, prng, itype=np.uint64):
     """Held-out counts per fold.
 

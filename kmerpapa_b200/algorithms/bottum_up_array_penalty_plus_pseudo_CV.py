@@ -123,6 +123,15 @@ class GpuFoldRunner:
         self.Mf, self.Uf = Mf, Uf
         self.folds = {}
 
+    def begin_folds(self, nkmer, nfolds):
+        """Folds arrive one at a time (set_fold) while earlier folds' jobs already run."""
+        self.Mf = np.zeros((nkmer, nfolds), dtype=np.uint64)
+        self.Uf = np.zeros((nkmer, nfolds), dtype=np.uint64)
+        self.folds = {}
+
+    def set_fold(self, f, M, U):
+        self.Mf[:, f], self.Uf[:, f] = M, U
+
     def _fold(self, f):
         if f not in self.folds:
             kM, kU = self.plan.pack_counts(self.codes, self.Mf[:, f], self.Uf[:, f], name="cvfold_k")
@@ -157,6 +166,54 @@ def run_grid(gen_pat, kmers, codes, pos, neg, alphas, penalties, nfolds, nit, se
     for it in range(nit):
         if verbosity > 0 and nit > 1:
             print("CV Iteration", it, file=sys.stderr)
+        jlo, jhi = max(lo, it * nfolds * na * npen), min(hi, (it + 1) * nfolds * na * npen)
+        if presampled is None and hasattr(runner, "set_fold"):
+            # The host sampler (numpy's legacy RandomState, about 0.3 s per fold for 9-mers) runs on a thread, one
+            # fold ahead of the GPU: the jobs are fold-major and fold f is final once drawn.  A fold's beta needs the
+            # fold's own totals and the grand totals only, and the latter are known beforehand (H7 quirk included).
+            import queue
+            import threading
+
+            q = queue.Queue()
+
+            def produce(prng=prng):
+                try:
+                    for item in CV_tools.iter_fold_counts(kmers, pos, neg, nfolds, prng):
+                        q.put(item)
+                except BaseException as e:   # surface sampler errors in the consumer
+                    q.put(e)
+
+            th = threading.Thread(target=produce, daemon=True)
+            th.start()
+            M_tot, U_tot = np.uint64(int(np.sum(pos))), np.uint64(int(np.sum(neg)))
+            if prev_M is not None:
+                M_tot = M_tot + np.uint64(cover - 1) * prev_M.sum()
+                U_tot = U_tot + np.uint64(cover - 1) * prev_U.sum()
+            runner.begin_folds(len(kmers), nfolds)
+            cur_M, cur_U = np.zeros(nfolds, dtype=np.uint64), np.zeros(nfolds, dtype=np.uint64)
+            j = jlo
+            for _ in range(nfolds):
+                item = q.get()
+                if isinstance(item, BaseException):
+                    raise item
+                f, M, U = item
+                runner.set_fold(f, M, U)
+                cur_M[f], cur_U[f] = M.sum(), U.sum()
+                mt, ut = cur_M[f], cur_U[f]
+                if prev_M is not None:
+                    mt, ut = mt + np.uint64(cover - 1) * prev_M[f], ut + np.uint64(cover - 1) * prev_U[f]
+                Mtr, Utr = np.array([M_tot - mt]), np.array([U_tot - ut])
+                while j < jhi and jobs[j][1] == f:
+                    _, _, a_i, p_i = jobs[j]
+                    beta = get_betas(alphas[a_i], Mtr, Utr)[0]
+                    tr, te = runner.run(f, alphas[a_i], beta, penalties[p_i])
+                    local[j - lo, 0], local[j - lo, 1] = tr, te
+                    j += 1
+            th.join()
+            prev_M, prev_U = cur_M, cur_U
+            if verbosity > 0:
+                print("CV sampling DONE", file=sys.stderr)
+            continue
         if presampled is not None:
             Mf, Uf = presampled[it]
         else:
@@ -175,7 +232,7 @@ def run_grid(gen_pat, kmers, codes, pos, neg, alphas, penalties, nfolds, nit, se
         U_sum_train = U_sum_test.sum() - U_sum_test
         betas = [get_betas(alpha, M_sum_train, U_sum_train) for alpha in alphas]
         runner.set_folds(Mf, Uf)
-        for j in range(max(lo, it * nfolds * na * npen), min(hi, (it + 1) * nfolds * na * npen)):
+        for j in range(jlo, jhi):
             _, f, a_i, p_i = jobs[j]
             tr, te = runner.run(f, alphas[a_i], betas[a_i][f], penalties[p_i])
             local[j - lo, 0], local[j - lo, 1] = tr, te

@@ -16,14 +16,10 @@ from ..engine import get_plan
 
 def kmer_arrays(contextD, index_mut=0):
     """contextD {kmer: (n_pos, ..., n_neg)} -> packed codes and int64 count columns."""
-    n = len(contextD)
-    codes = np.empty(n, dtype=np.uint64)
-    pos = np.empty(n, dtype=np.int64)
-    neg = np.empty(n, dtype=np.int64)
-    for r, (kmer, tup) in enumerate(contextD.items()):
-        codes[r] = iupac.kmer_code(kmer)
-        pos[r] = tup[index_mut]
-        neg[r] = tup[-1]
+    codes = iupac.kmer_codes(contextD.keys())
+    vals = list(contextD.values())
+    pos = np.array([t[index_mut] for t in vals], dtype=np.int64)
+    neg = np.array([t[-1] for t in vals], dtype=np.int64)
     return codes, pos, neg
 
 

@@ -15,8 +15,11 @@ def _to_count(text):
         return int(float(text))
 
 
+_NO_ACGT = {ord(c): None for c in "ACGT"}
+
+
 def _is_plain_kmer(kmer):
-    return all(c in iupac.NUCLEOTIDES for c in kmer)
+    return not kmer.translate(_NO_ACGT)   # nothing is left once A, C, G, T are deleted
 
 
 def _centre_window(have, want):

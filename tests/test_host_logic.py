@@ -79,6 +79,57 @@ def test_fold_sampler_matches_reference_stream(oracle, path):
     assert np.array_equal(Mf2, Mf[perm]) and np.array_equal(Uf2, Uf[perm])
 
 
+def test_streaming_sampler_equals_batch_sampler():
+    """iter_fold_counts (one fold at a time, feeds the GPU while the next fold is drawn) == sample_fold_counts."""
+    from kmerpapa_b200 import CV_tools, iupac
+
+    kmers = iupac.matches("NNRN")
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(len(kmers))
+    kmers = [kmers[i] for i in perm]
+    pos, neg = rng.integers(0, 50, len(kmers)), rng.integers(0, 5000, len(kmers))
+    for nf in (2, 3, 5):
+        Mf, Uf = CV_tools.sample_fold_counts(kmers, pos, neg, nf, np.random.RandomState(5))
+        seen = []
+        for f, M, U in CV_tools.iter_fold_counts(kmers, pos, neg, nf, np.random.RandomState(5)):
+            seen.append(f)
+            assert np.array_equal(M, Mf[:, f]) and np.array_equal(U, Uf[:, f])
+        assert seen == list(range(nf))
+
+
+def test_pipelined_grid_equals_batch_grid():
+    """run_grid with a runner that accepts folds one at a time (the GPU runner's interface) gives the results of
+    the batch path, H7 quirk of later iterations included."""
+    from kmerpapa_b200 import iupac
+    from kmerpapa_b200.algorithms import bottum_up_array_penalty_plus_pseudo_CV as cv
+
+    class Batch:
+        def set_folds(self, Mf, Uf):
+            self.Mf, self.Uf = Mf, Uf
+
+        def run(self, f, alpha, beta, penalty):   # a stand-in "DP": any deterministic function of its inputs
+            x = float(self.Mf[:, f].sum()) * alpha + float(self.Uf[:, f].sum()) * 1e-3 + beta * penalty
+            return np.float32(x), np.float32(x / 3)
+
+    class Streaming(Batch):
+        def begin_folds(self, nkmer, nfolds):
+            self.Mf = np.zeros((nkmer, nfolds), dtype=np.uint64)
+            self.Uf = np.zeros((nkmer, nfolds), dtype=np.uint64)
+
+        def set_fold(self, f, M, U):
+            self.Mf[:, f], self.Uf[:, f] = M, U
+
+    gp = "NNMN"
+    kmers = iupac.matches(gp)
+    rng = np.random.default_rng(1)
+    pos, neg = rng.integers(0, 30, len(kmers)), rng.integers(100, 9000, len(kmers))
+    codes = iupac.kmer_codes(kmers)
+    for nit in (1, 3):
+        a = cv.run_grid(gp, kmers, codes, pos, neg, [0.5, 2.0], [3.0, 5.0], 4, nit, 9, runner=Batch(), gather_device=None)
+        b = cv.run_grid(gp, kmers, codes, pos, neg, [0.5, 2.0], [3.0, 5.0], 4, nit, 9, runner=Streaming(), gather_device=None)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 def test_fold_sums_like_reference_test():
     """tests/test_CV_tools.py of the reference: folds add back to the table."""
     from kmerpapa_b200 import CV_tools
