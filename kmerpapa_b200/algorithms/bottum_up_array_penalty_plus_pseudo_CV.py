@@ -148,9 +148,11 @@ class GpuFoldRunner:
 
 
 def run_grid(gen_pat, kmers, codes, pos, neg, alphas, penalties, nfolds, nit, seed, verbosity=0, runner=None,
-             gather_device="auto", presampled=None):
+             gather_device="auto", presampled=None, progress=None):
     """Core of the CV: returns float32 results [nit, nfolds, n_alpha, n_penalty, 2] (train, held-out).
-    presampled: optional list (one per iteration) of (Mf, Uf) held-out tables to use instead of sampling."""
+    presampled: optional list (one per iteration) of (Mf, Uf) held-out tables to use instead of sampling.
+    progress(it, results_of_iteration): called once per iteration, in order — right after the iteration's jobs in
+    a single process (the reference's interleaving of its stderr lines), after the gather when the jobs are sharded."""
     rank, world = dist_info()
     prng = np.random.RandomState(seed)
     if runner is None:
@@ -213,6 +215,8 @@ def run_grid(gen_pat, kmers, codes, pos, neg, alphas, penalties, nfolds, nit, se
             prev_M, prev_U = cur_M, cur_U
             if verbosity > 0:
                 print("CV sampling DONE", file=sys.stderr)
+            if progress is not None and world == 1:
+                progress(it, local.reshape(nit, nfolds, na, npen, 2)[it])
             continue
         if presampled is not None:
             Mf, Uf = presampled[it]
@@ -236,8 +240,13 @@ def run_grid(gen_pat, kmers, codes, pos, neg, alphas, penalties, nfolds, nit, se
             _, f, a_i, p_i = jobs[j]
             tr, te = runner.run(f, alphas[a_i], betas[a_i][f], penalties[p_i])
             local[j - lo, 0], local[j - lo, 1] = tr, te
-    full = gather_job_results(local, len(jobs), rank, world, gather_device)
-    return full.reshape(nit, nfolds, na, npen, 2)
+        if progress is not None and world == 1:
+            progress(it, local.reshape(nit, nfolds, na, npen, 2)[it])
+    full = gather_job_results(local, len(jobs), rank, world, gather_device).reshape(nit, nfolds, na, npen, 2)
+    if progress is not None and world > 1:
+        for it in range(nit):
+            progress(it, full[it])
+    return full
 
 
 def pattern_partition_bottom_up(gen_pat, contextD, alphas, args, nmut, nunmut, penalties, index_mut=0):
@@ -247,15 +256,17 @@ def pattern_partition_bottom_up(gen_pat, contextD, alphas, args, nmut, nunmut, p
     kmers = list(contextD.keys())
     codes, pos, neg = kmer_arrays(contextD, index_mut)
     verbosity = getattr(args, "verbosity", 0)
-    results = run_grid(gen_pat, kmers, codes, pos, neg, alphas, penalties, nf, nit, args.seed, verbosity)
     rank, _ = dist_info()
-    if verbosity > 0 and rank == 0:
-        for it in range(nit):
+
+    def progress(it, res_it):   # the reference's per-grid-point lines (_CV.py:157-160)
+        if verbosity > 0 and rank == 0:
             for a_i, alpha in enumerate(alphas):
                 for p_i, penalty in enumerate(penalties):
-                    row = results[it, :, a_i, p_i, 1]
+                    row = res_it[:, a_i, p_i, 1]
                     print(f"CV on k={len(gen_pat)} alpha={alpha} penalty={penalty} i={it} test_LL={sum(row)}", file=sys.stderr)
                     if verbosity > 1:
                         print(f"test LL for each fold: {row}", file=sys.stderr)
+
+    results = run_grid(gen_pat, kmers, codes, pos, neg, alphas, penalties, nf, nit, args.seed, verbosity, progress=progress)
     cvfile = args.CVfile if rank == 0 else None
     return select_best(alphas, penalties, results, nit, nf, len(gen_pat), cvfile)
