@@ -257,12 +257,16 @@ def pattern_partition_bottom_up(gen_pat, contextD, alphas, args, nmut, nunmut, p
     codes, pos, neg = kmer_arrays(contextD, index_mut)
     verbosity = getattr(args, "verbosity", 0)
     rank, _ = dist_info()
+    gen_pat_level = iupac.pattern_level(gen_pat)
 
     def progress(it, res_it):   # the reference's per-grid-point lines (_CV.py:157-160)
         if verbosity > 0 and rank == 0:
             for a_i, alpha in enumerate(alphas):
                 for p_i, penalty in enumerate(penalties):
                     row = res_it[:, a_i, p_i, 1]
+                    if verbosity > 1:   # the reference reports every level of every grid point's DP (_CV.py:154-155)
+                        for level in range(1, gen_pat_level + 1):
+                            print(f"level {level} of {gen_pat_level}", file=sys.stderr)
                     print(f"CV on k={len(gen_pat)} alpha={alpha} penalty={penalty} i={it} test_LL={sum(row)}", file=sys.stderr)
                     if verbosity > 1:
                         print(f"test LL for each fold: {row}", file=sys.stderr)
