@@ -41,7 +41,9 @@ struct kp_plan {
     uint32_t *d_tiles = nullptr;
     uint8_t *d_genmask = nullptr;
     int *d_err = nullptr;
-    uint32_t *d_counters = nullptr;  // one tile counter per wave
+    uint32_t *d_counters = nullptr;  // one tile counter per wave, then (single-launch mode) 64 finished-tile counters
+    uint8_t *d_tile_wave = nullptr;  // single-launch mode: wave of every entry of d_tiles
+    uint8_t *d_tile_done = nullptr;  // single-launch mode: per-tile completion flags
     unsigned char *d_scratch = nullptr;  // staging for the small host<->device exchanges (grown on demand)
     size_t scratch_cap = 0;
     uint64_t launches = 0;
@@ -147,7 +149,15 @@ int kp_plan_create(const char *gen_pat, int device, kp_plan **out)
     KP_CUDA(cudaMemcpy(p->d_genmask, p->host.gen_mask, KP_MAXK, cudaMemcpyHostToDevice));
     KP_CUDA(cudaMalloc(&p->d_err, sizeof(int)));
     KP_CUDA(cudaMemset(p->d_err, 0, sizeof(int)));
-    KP_CUDA(cudaMalloc(&p->d_counters, sizeof(uint32_t) * 64));
+    KP_CUDA(cudaMalloc(&p->d_counters, sizeof(uint32_t) * 128));
+    if (t.r0 == 15 && t.nhigh > 0) {
+        std::vector<uint8_t> tw(p->host.tile_order.size());
+        for (size_t l = 0; l + 1 < p->host.hl_off.size(); l++)
+            for (uint64_t i = p->host.hl_off[l]; i < p->host.hl_off[l + 1]; i++) tw[i] = (uint8_t)l;
+        KP_CUDA(cudaMalloc(&p->d_tile_wave, tw.size()));
+        KP_CUDA(cudaMemcpy(p->d_tile_wave, tw.data(), tw.size(), cudaMemcpyHostToDevice));
+        KP_CUDA(cudaMalloc(&p->d_tile_done, tw.size()));
+    }
     p->smem_optin = prop.sharedMemPerBlockOptin;
     for (int wide = 0; wide < 2; wide++) {
         size_t fixed = 2048 + t.rt_bytes, per_warp = t.warp_smem_bytes[wide];
@@ -157,6 +167,9 @@ int kp_plan_create(const char *gen_pat, int device, kp_plan **out)
         // the attribute is per function, not per plan: always raise it to the device maximum
         KP_CUDA(cudaFuncSetAttribute(dp_kernel_ptr(t.r0, t.rp, wide), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)prop.sharedMemPerBlockOptin));
+        if (t.r0 == 15)
+            KP_CUDA(cudaFuncSetAttribute(wide ? dp_kernel_sharded<true, 3>(t.rp) : dp_kernel_sharded<false, 3>(t.rp),
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     }
     *out = p;
     return 0;
@@ -172,6 +185,8 @@ int kp_plan_destroy(kp_plan *p)
     cudaFree(p->d_genmask);
     cudaFree(p->d_err);
     cudaFree(p->d_counters);
+    cudaFree(p->d_tile_wave);
+    cudaFree(p->d_tile_done);
     cudaFree(p->d_scratch);
     delete p;
     return 0;
@@ -304,7 +319,27 @@ static int launch_dp(kp_plan *p, bool wide, KpDpParams prm, cudaStream_t st)
     size_t nhl = p->host.hl_off.size() - 1;
     const KpTables &t = p->host.t;
     if (nhl > 64) return fail("too many tile waves");
-    KP_CUDA(cudaMemsetAsync(p->d_counters, 0, sizeof(uint32_t) * 64, st));
+    KP_CUDA(cudaMemsetAsync(p->d_counters, 0, sizeof(uint32_t) * 128, st));
+    // Large all-N problems: ONE launch over every wave; tiles wait for their child tiles, not for a kernel boundary
+    if (p->d_tile_done && t.ntiles >= (uint64_t)8 * p->sm_count * nw && !getenv("KP_WAVE_LAUNCHES")) {
+        KP_CUDA(cudaMemsetAsync(p->d_tile_done, 0, t.ntiles, st));
+        KP_CUDA(cudaMemsetAsync(p->d_err, 0, sizeof(int), st));
+        prm.tile_list = p->d_tiles;
+        prm.ntiles_wave = (uint32_t)t.ntiles;
+        prm.counter = p->d_counters;
+        prm.leaf_wave = 0;
+        prm.tile_wave = p->d_tile_wave;
+        prm.tile_done = p->d_tile_done;
+        prm.wave_done = p->d_counters + 64;
+        prm.err = p->d_err;
+        for (size_t l = 0; l < 64; l++) prm.wave_size[l] = l < nhl ? (uint32_t)(p->host.hl_off[l + 1] - p->host.hl_off[l]) : 0;
+        const size_t sm = 2048 + t.rt_bytes + (size_t)nw * t.warp_smem_bytes[wide];
+        if (t.rp == KP_RP_NN) launch_dp_r0<15, KP_RP_NN, 3>(wide, p->sm_count, nw * 32, sm, st, prm);
+        else launch_dp_r0<15, 0, 3>(wide, p->sm_count, nw * 32, sm, st, prm);
+        p->launches++;
+        KP_CUDA(cudaGetLastError());
+        return 0;
+    }
     for (size_t l = 0; l < nhl; l++) {
         uint64_t lo = p->host.hl_off[l], hi = p->host.hl_off[l + 1];
         if (hi == lo) continue;
@@ -395,8 +430,11 @@ int kp_backtrack(kp_plan *p, const float *d_best, const uint16_t *d_kept, void *
     float *vals;
     if (backtrack_device(p, single_view(p, d_best, d_kept), d_ws, cap, root, st, &sorted, &keys, &vals, &ctr)) return 1;
     unsigned long long hc[2] = {0, 0};
+    int herr = 0;
     KP_CUDA(cudaMemcpyAsync(hc, ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaMemcpyAsync(&herr, p->d_err, sizeof herr, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaStreamSynchronize(st));
+    if (herr == 2) return fail("kp_backtrack: the DP gave up waiting for a child tile (internal error)");
     *n_out = hc[0];
     if (hc[1] || hc[0] > cap) return fail("kp_backtrack: partition larger than the workspace capacity");
     KP_CUDA(cudaMemcpyAsync(h_patnums, sorted, hc[0] * 8, cudaMemcpyDeviceToHost, st));

@@ -195,6 +195,13 @@ struct KpDpParams {
     uint16_t *flags;            // per row, bit d set = pattern kept whole
     KpView view;                // sharded DP only: every rank's shard, for the child tiles of the top position
     int my_rank;
+    // single-launch mode (SHARD == 3): all waves in one launch, a tile waits for its child tiles instead of a
+    // kernel boundary, so the tail of one wave overlaps the head of the next
+    const uint8_t *tile_wave;   // wave of every entry of tile_list
+    uint8_t *tile_done;         // [ntiles] 1 once a tile's rows are stored (zeroed before the launch)
+    uint32_t *wave_done;        // [64] finished tiles per wave (zeroed before the launch)
+    uint32_t wave_size[64];     // tiles per wave
+    int *err;                   // set when a dependency wait gives up (never expected)
 };
 
 // RP: the row pitch as a compile-time constant (0: read it from the tables).  With the pitch known, the tile
@@ -205,6 +212,9 @@ struct KpDpParams {
 //     rank in their top 4 bits).
 //   2 (replicated, speed): every rank holds a full-size table; a finished row is stored locally AND into the
 //     table of every peer that owns a superset digit (posted NVLink writes), so all reads stay local.
+//   3 (one GPU, single launch): tile_list holds every wave back to back and tiles are claimed in that order by the
+//     resident warps (one CTA per SM, all resident); a tile spins until its child tiles are flagged done.  Claiming
+//     in order makes this deadlock-free: every child was claimed earlier, by a warp that is running.
 template <int R0, bool WIDE, int RP, int SHARD>
 __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const KpDpParams p)
 {
@@ -212,6 +222,7 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
     constexpr int NG = (R0 + 3) / 4;
     constexpr int NB = R0 == 15 ? 4 : (R0 == 7 ? 3 : (R0 == 3 ? 2 : 1));
     constexpr bool SHARDED = SHARD == 1;   // partitioned addressing
+    constexpr bool ONE_LAUNCH = SHARD == 3;
 
     extern __shared__ __align__(16) unsigned char smem[];
     const KpTables &tb = *p.tab;
@@ -252,6 +263,8 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
         it = __shfl_sync(0xffffffffu, it, 0);
         if (it >= p.ntiles_wave) break;
         const uint32_t tile = p.tile_list[it];
+        const int wave = ONE_LAUNCH ? (int)p.tile_wave[it] : 0;
+        const bool leaf_tile = ONE_LAUNCH ? wave == 0 : (p.leaf_wave != 0);
         uint32_t ltile = tile;   // index of the tile in this rank's table
         if (SHARDED) {
             const uint32_t dt = tile / p.view.hw_top;
@@ -292,6 +305,33 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
                 }
             }
             if (lane == 0) *s_nhs = total;
+        }
+        if (ONE_LAUNCH && wave > 0) {
+            // ---- wait for the child tiles.  They sit at most three waves back (a split lowers one position by at
+            //      most three levels): if those waves are complete nothing needs checking ----
+            bool all_done = true;
+            if (lane < 3 && wave - 1 - lane >= 0) {
+                const int w = wave - 1 - lane;
+                uint32_t c;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(p.wave_done + w) : "memory");
+                all_done = c == p.wave_size[w];
+            }
+            all_done = __all_sync(0xffffffffu, all_done);   // one decision for the warp
+            if (!all_done) {
+                __syncwarp();   // split lists written by the other lanes
+                const int n2 = 2 * *s_nhs;
+                for (int j = lane; j < n2; j += 32) {
+                    const uint32_t child = j & 1 ? hs2[j >> 1] : hs1[j >> 1];
+                    unsigned spins = 0;
+                    for (;;) {
+                        uint32_t f;
+                        asm volatile("ld.acquire.gpu.global.u8 %0, [%1];" : "=r"(f) : "l"(p.tile_done + child) : "memory");
+                        if (f) break;
+                        if (++spins > (1u << 22)) { atomicExch(p.err, 2); break; }
+                        __nanosleep(200);
+                    }
+                }
+            }
         }
         // ---- base counts of the tile ----
         for (uint32_t kl = lane; kl < tk; kl += 32) {
@@ -348,7 +388,10 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
             a_ = (const float4 *)p.view.best[h1_ >> 28] + lrowc + (size_t)(h1_ & 0x0fffffffu) * stride4; \
             b_ = (const float4 *)p.view.best[h2_ >> 28] + lrowc + (size_t)(h2_ & 0x0fffffffu) * stride4; \
         }                                                                                             \
-        _Pragma("unroll") for (int g = 0; g < NG; g++) { xa[g] = __ldg(a_ + g * rp); xb[g] = __ldg(b_ + g * rp); } \
+        _Pragma("unroll") for (int g = 0; g < NG; g++) {   /* single launch: the table is written by this kernel, no .nc */ \
+            xa[g] = ONE_LAUNCH ? __ldcg(a_ + g * rp) : __ldg(a_ + g * rp);                            \
+            xb[g] = ONE_LAUNCH ? __ldcg(b_ + g * rp) : __ldg(b_ + g * rp);                            \
+        }                                                                                             \
         if (++ls == nhs) {                                                                            \
             ls = 0; lrow += 32;                                                                       \
             lrowc = lrow < nrows ? lrow : nrows - 1;                                                  \
@@ -461,7 +504,7 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
                     }
                 }
                 // ---- score filter: which patterns can still be kept whole? (v only decreases from here) ----
-                const bool leafrow = p.leaf_wave && row_level[srow] == 0;
+                const bool leafrow = leaf_tile && row_level[srow] == 0;
                 uint32_t need = 0;
                 {
                     float mf[NB], uf[NB];
@@ -564,6 +607,14 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
                 }
             }
             __syncwarp();  // rows of this round visible to the warp
+        }
+        if (ONE_LAUNCH) {   // publish the tile: every lane's stores, then the flag and the wave counter
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("st.release.gpu.global.u8 [%0], %1;" ::"l"(p.tile_done + tile), "r"(1u) : "memory");
+                atomicAdd(p.wave_done + wave, 1u);
+            }
         }
     }
 }
