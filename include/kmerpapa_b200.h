@@ -204,6 +204,13 @@ int kp_shard_backtrack(kp_shard *shard, void *d_ws, uint64_t cap, uint64_t root,
 int kp_shard_gather(kp_shard *shard, const uint64_t *h_patnums, uint64_t n, float *h_best, uint8_t *h_kept,
                     uint8_t *h_codes, void *stream);
 
+/* The all-k-mers model (reference: all_kmers_CV.py:8-13, :42-43; `--score all_kmers`): for n (k-mer, fold) items with
+ * train counts (Mtr, Utr), held-out counts (Mte, Ute) and the fold's beta, the float64 terms
+ *   train = -2 (xlogy(Mtr, p) + xlog1py(Utr, -p)),  test = -2 (xlogy(Mte, p) + xlog1py(Ute, -p)),
+ *   p = (Mtr + alpha) / (Mtr + Utr + alpha + beta), bit for bit as numpy/scipy evaluate them.  Host buffers. */
+int kp_kmer_fold_terms(int device, const int64_t *h_Mtr, const int64_t *h_Utr, const int64_t *h_Mte, const int64_t *h_Ute,
+                       const double *h_beta, uint64_t n, double alpha, double *h_train, double *h_test);
+
 /* Test hook: y[i] = device log(x[i]) (the glibc-exact restatement used by the scoring kernels). */
 int kp_debug_log(int device, const double *h_x, double *h_y, uint64_t n);
 /* Test hook: level-0 score of (M,U) pairs on the device (scipy xlogy/xlog1py restated). */

@@ -48,14 +48,16 @@ def iter_fold_counts(kmers, pos, neg, nfolds, prng, itype=np.uint64):
         yield f, M, U
 
 
-def sample_fold_counts(kmers, pos, neg, nfolds, prng, itype=np.uint64):
+def sample_fold_counts(kmers, pos, neg, nfolds, prng, itype=np.uint64, sort=True):
     """Held-out counts per fold.
 
     kmers: list of k-mer strings; pos/neg: their counts (same order).
     Returns (Mf, Uf), arrays [len(kmers), nfolds] in the order of `kmers`.
+    sort=True: urn colours in sorted k-mer order (the pattern-partition CV, CV_tools.py:42-43 of the reference);
+    sort=False: in the given order (the all-k-mers CV enumerates `matches(gen_pat)`, :75).
     """
     n = len(kmers)
-    order = sorted(range(n), key=kmers.__getitem__)
+    order = sorted(range(n), key=kmers.__getitem__) if sort else list(range(n))
     urn = np.empty(2 * n, dtype=itype)
     for r, i in enumerate(order):
         urn[r] = pos[i]

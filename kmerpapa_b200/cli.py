@@ -6,8 +6,8 @@ calls (cli.py:232 and :279): they go to kmerpapa_b200.algorithms (CUDA), and the
 of the output rows come from the device k-mer tables (kp_pattern_counts) instead of the reference's
 Python enumeration (pattern_utils.get_M_U, cli.py:281-283).
 
-Out of scope in this build: --greedy, --greedyCV, --BayesOpt and --score all_kmers are
-accepted by the parser like in the reference but stop with a clear error instead of running.
+`--score all_kmers` goes to kmerpapa_b200.algorithms.all_kmers_CV.  Out of scope in this build:
+--greedy, --greedyCV and --BayesOpt are accepted by the parser like in the reference but stop with a clear error.
 """
 import argparse
 import sys
@@ -137,9 +137,9 @@ def main(args=None):
         return 0
     if args.verbosity > 0:
         print(f"Input data read. {n_mut} positive k-mers and {n_unmut} negative k-mers", file=sys.stderr)
-    if args.greedy or args.greedyCV or args.BayesOpt or args.score == "all_kmers":
-        raise SystemExit("kmerpapa_b200 implements the optimal pattern partition only: --greedy, --greedyCV, --BayesOpt "
-                         "and --score all_kmers belong to the reference's other estimators and are not part of this build")
+    if args.greedy or args.greedyCV or args.BayesOpt:
+        raise SystemExit("kmerpapa_b200 implements the optimal pattern partition (and the all-k-mers model): --greedy, "
+                         "--greedyCV and --BayesOpt belong to the reference's greedy estimator and are not part of this build")
     if args.penalty_values is not None:
         assert args.score == "penalty_and_pseudo", \
             f"you cannot specify penalty values when using the {args.score} score function"
@@ -157,7 +157,7 @@ def main(args=None):
     if args.CVfile is not None:
         print("k alpha P LL_test", file=args.CVfile)
 
-    from .algorithms import bottum_up_array_penalty_plus_pseudo_CV, bottum_up_array_w_numba
+    from .algorithms import all_kmers_CV, bottum_up_array_penalty_plus_pseudo_CV, bottum_up_array_w_numba
 
     best_alpha = best_penalty = best_k = None
     ks = range(len(gen_pat), 1, -2) if args.test_smaller_k else [len(gen_pat)]
@@ -171,8 +171,13 @@ def main(args=None):
                 print(f"Running {args.nfolds}-fold cross validation on {k}-mers", file=sys.stderr)
             if k != len(this_gen_pat):
                 this_contextD, this_gen_pat = downsize_contextD(this_contextD, this_gen_pat, k)
-            this_alpha, this_penalty, test_score = bottum_up_array_penalty_plus_pseudo_CV.pattern_partition_bottom_up(
-                this_gen_pat, this_contextD, args.pseudo_counts, args, n_mut, n_unmut, args.penalty_values)
+            if args.score == "all_kmers":
+                this_alpha, test_score = all_kmers_CV.all_kmers(this_gen_pat, this_contextD, args.pseudo_counts, args,
+                                                                n_mut, n_unmut)
+                this_penalty = None
+            else:
+                this_alpha, this_penalty, test_score = bottum_up_array_penalty_plus_pseudo_CV.pattern_partition_bottom_up(
+                    this_gen_pat, this_contextD, args.pseudo_counts, args, n_mut, n_unmut, args.penalty_values)
             with np.errstate(over="ignore"):   # np.float32 against the 1e100 start value, as in the reference
                 better = test_score < best_score
             if better:
@@ -188,7 +193,7 @@ def main(args=None):
     if best_alpha is None:
         assert len(args.pseudo_counts) == 1
         best_alpha = args.pseudo_counts[0]
-    if best_penalty is None:
+    if args.score != "all_kmers" and best_penalty is None:
         assert len(args.penalty_values) == 1
         best_penalty = args.penalty_values[0]
     if best_k is None:
@@ -199,9 +204,13 @@ def main(args=None):
     if args.verbosity > 0:
         print(f"Training on whole data set with k={best_k} alpha={best_alpha} penalty={best_penalty}", file=sys.stderr)
 
-    best_score, M, U, names = bottum_up_array_w_numba.pattern_partition_bottom_up(
-        gen_pat, contextD, best_alpha, best_beta, best_penalty, args, n_mut, n_unmut)
-    counts = _pattern_counts(gen_pat, contextD, names)
+    if args.score == "all_kmers":   # every k-mer is its own pattern (cli.py:267-272 of the reference)
+        best_score, M, U, names = 0, n_mut, n_unmut, list(iupac.matches(gen_pat))
+        counts = [tuple(contextD[k][:2]) for k in names]
+    else:
+        best_score, M, U, names = bottum_up_array_w_numba.pattern_partition_bottom_up(
+            gen_pat, contextD, best_alpha, best_beta, best_penalty, args, n_mut, n_unmut)
+        counts = _pattern_counts(gen_pat, contextD, names)
     assert M == n_mut
     assert U == n_unmut
     assert n_mut == sum(x[0] for x in counts)

@@ -852,6 +852,30 @@ int kp_shard_gather(kp_shard *s, const uint64_t *h_patnums, uint64_t n, float *h
     return 0;
 }
 
+int kp_kmer_fold_terms(int device, const int64_t *h_Mtr, const int64_t *h_Utr, const int64_t *h_Mte, const int64_t *h_Ute,
+                       const double *h_beta, uint64_t n, double alpha, double *h_train, double *h_test)
+{
+    if (!h_Mtr || !h_Utr || !h_Mte || !h_Ute || !h_beta || !h_train || !h_test) return fail("kp_kmer_fold_terms: null argument");
+    if (n == 0) return 0;
+    KP_CUDA(cudaSetDevice(device));
+    long long *d_in = nullptr;
+    double *d_f = nullptr;
+    KP_CUDA(cudaMalloc(&d_in, n * 8 * 4));
+    cudaError_t e = cudaMalloc(&d_f, n * 8 * 3);
+    if (e != cudaSuccess) { cudaFree(d_in); return fail("kp_kmer_fold_terms: out of device memory"); }
+    const int64_t *src[4] = {h_Mtr, h_Utr, h_Mte, h_Ute};
+    for (int i = 0; i < 4; i++) cudaMemcpy(d_in + i * n, src[i], n * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_f, h_beta, n * 8, cudaMemcpyHostToDevice);
+    kp_kmer_fold_terms_kernel<<<296, 256>>>(d_in, d_in + n, d_in + 2 * n, d_in + 3 * n, d_f, n, alpha, d_f + n, d_f + 2 * n);
+    cudaError_t e2 = cudaGetLastError();
+    cudaMemcpy(h_train, d_f + n, n * 8, cudaMemcpyDeviceToHost);
+    cudaError_t e3 = cudaMemcpy(h_test, d_f + 2 * n, n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    cudaFree(d_f);
+    if (e2 != cudaSuccess || e3 != cudaSuccess) return fail(std::string("kp_kmer_fold_terms: ") + cudaGetErrorString(e2 != cudaSuccess ? e2 : e3));
+    return 0;
+}
+
 int kp_debug_log(int device, const double *h_x, double *h_y, uint64_t n)
 {
     KP_CUDA(cudaSetDevice(device));

@@ -1055,6 +1055,23 @@ __global__ void kp_debug_log_kernel(const double *x, double *y, unsigned long lo
         y[i] = kp_log(x[i], tab);
 }
 
+// per-(k-mer, fold) terms of the all-k-mers model (all_kmers_CV.py:8-13, :42-43): the level-0 formulas with no penalty
+__global__ void kp_kmer_fold_terms_kernel(const long long *Mtr, const long long *Utr, const long long *Mte, const long long *Ute,
+                                          const double *beta, unsigned long long n, double alpha, double *train, double *test)
+{
+    __shared__ double2 tab[128];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) tab[i] = make_double2(kpc_logTab[2 * i], kpc_logTab[2 * i + 1]);
+    __syncthreads();
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        double a, b;
+        kp_leaf_cv((unsigned long long)Mtr[i], (unsigned long long)Utr[i], (unsigned long long)Mte[i], (unsigned long long)Ute[i],
+                   alpha, beta[i], 0.0, tab, a, b);
+        train[i] = a;
+        test[i] = b;
+    }
+}
+
 __global__ void kp_debug_leaf_kernel(const long long *M, const long long *U, unsigned long long n, double alpha,
                                      double beta, double penalty, double *out)
 {

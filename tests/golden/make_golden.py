@@ -324,6 +324,10 @@ def make_cli(which):
         argv = ["-p", f"{d}/mutated_5mers.txt", "-b", f"{d}/background_5mers.txt", "-c", "3", "5", "--seed", "1",
                 "--verbosity", "2"]
         run_worker("cli", {"argv": argv}, os.path.join(HERE, "cli_5mers_verbose.json"))
+    elif which == "cli5_allkmers":   # --score all_kmers: CV over pseudo counts of the one-rate-per-k-mer model
+        argv = ["-p", f"{d}/mutated_5mers.txt", "-b", f"{d}/background_5mers.txt", "--score", "all_kmers",
+                "-a", "0.5", "1", "10", "--nfolds", "3", "--seed", "2"]
+        run_worker("cli", {"argv": argv, "cvfile": False}, os.path.join(HERE, "cli_5mers_all_kmers.json"))
     elif which == "cli5_scores":   # the information-criterion penalties (--score BIC)
         argv = ["-p", f"{d}/mutated_5mers.txt", "-b", f"{d}/background_5mers.txt", "--score", "BIC", "-a", "1"]
         run_worker("cli", {"argv": argv, "cvfile": False}, os.path.join(HERE, "cli_5mers_BIC.json"))
@@ -358,7 +362,7 @@ def main():
             make_small()
         if w == "all":
             for c in ("cli5", "cli5_single", "cli5_sp", "cli5_negative", "cli5_joint", "cli5_trim", "cli5_smallerk",
-                      "cli5_iter2", "cli5_verbose", "cli5_scores", "cli7_single", "cli7"):
+                      "cli5_iter2", "cli5_verbose", "cli5_allkmers", "cli5_scores", "cli7_single", "cli7"):
                 make_cli(c)
         elif w.startswith("cli"):
             make_cli(w)
