@@ -204,6 +204,19 @@ int kp_shard_backtrack(kp_shard *shard, void *d_ws, uint64_t cap, uint64_t root,
 int kp_shard_gather(kp_shard *shard, const uint64_t *h_patnums, uint64_t n, float *h_best, uint8_t *h_kept,
                     uint8_t *h_codes, void *stream);
 
+/* Greedy top-down partition (reference: greedy_penalty_plus_pseudo.py:155-196 greedy_res_kmer_table_ord, :285-300
+ * greedy_partition, :318-337 CrossValidation.loglik).  Starting from the general pattern, a pattern is split at the
+ * first (string position, split) whose float64 sum of the two children's losses is the strict minimum below the
+ * pattern's own loss, else it becomes a leaf; children are expanded first child first.  Works on the dense k-mer
+ * tables of kp_pack_counts (no pattern table).  d_testM/d_testU (both or none): held-out k-mer tables; h_test then
+ * receives the held-out -2 log-likelihood of every leaf under the leaf's train rate (test_logLik, :26-34).
+ * Outputs: dense pattern numbers of the leaves in the reference's order, their float64 losses, and h_total = the
+ * float64 sum of the losses in the order of the recursion (the reference's returned score). */
+uint64_t kp_greedy_ws_bytes(uint64_t cap);
+int kp_greedy(kp_plan *plan, const int64_t *d_kmerM, const int64_t *d_kmerU, const int64_t *d_testM, const int64_t *d_testU,
+              double alpha, double beta, double penalty, void *d_ws, uint64_t cap, uint64_t *h_patnums, double *h_loss,
+              double *h_test, uint64_t *n_out, double *h_total, void *stream);
+
 /* The all-k-mers model (reference: all_kmers_CV.py:8-13, :42-43; `--score all_kmers`): for n (k-mer, fold) items with
  * train counts (Mtr, Utr), held-out counts (Mte, Ute) and the fold's beta, the float64 terms
  *   train = -2 (xlogy(Mtr, p) + xlog1py(Utr, -p)),  test = -2 (xlogy(Mte, p) + xlog1py(Ute, -p)),

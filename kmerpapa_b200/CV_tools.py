@@ -75,3 +75,21 @@ def sample_fold_counts(kmers, pos, neg, nfolds, prng, itype=np.uint64, sort=True
     Mf[inv] = draws[:n]
     Uf[inv] = draws[n:]
     return Mf, Uf
+
+
+def make_all_folds(kmer_table, n_folds, n_repeats, prng):
+    """Folds of a [n_kmers, 2] count table for the greedy estimator's CV (reference CV_tools.py:123-147): the urn
+    colours are the table's entries in row-major order (positive, negative of k-mer 0, then k-mer 1, ...), every
+    repeat deals the whole table again.  Returns [n_repeats, n_folds, n_kmers, 2]."""
+    itype = kmer_table.dtype
+    shape = kmer_table.shape
+    folds = np.zeros((n_repeats, n_folds) + shape, dtype=itype)
+    per_fold = kmer_table.sum() // n_folds
+    for i in range(n_repeats):
+        urn = np.copy(kmer_table).reshape(-1)
+        for j in range(n_folds - 1):
+            got = draw_multivariate_hypergeometric(per_fold, urn, prng)
+            urn -= got
+            folds[i][j] = got.reshape(shape)
+        folds[i][n_folds - 1] = urn.reshape(shape)
+    return folds

@@ -65,6 +65,9 @@ SYMBOLS = {
     "kp_shard_dp_wave": (_int, [_vp, _int, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp]),
     "kp_shard_backtrack": (_int, [_vp, _vp, _u64, _u64, _vp, ctypes.POINTER(_u64), _vp]),
     "kp_shard_gather": (_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp]),
+    "kp_greedy_ws_bytes": (_u64, [_u64]),
+    "kp_greedy": (_int, [_vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _vp, _u64, _vp, _vp, _vp, ctypes.POINTER(_u64),
+                         ctypes.POINTER(_dbl), _vp]),
     "kp_kmer_fold_terms": (_int, [_int, _vp, _vp, _vp, _vp, _vp, _u64, _dbl, _vp, _vp]),
     "kp_debug_log": (_int, [_int, _vp, _vp, _u64]),
     "kp_debug_leaf_score": (_int, [_int, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp]),

@@ -6,8 +6,9 @@ calls (cli.py:232 and :279): they go to kmerpapa_b200.algorithms (CUDA), and the
 of the output rows come from the device k-mer tables (kp_pattern_counts) instead of the reference's
 Python enumeration (pattern_utils.get_M_U, cli.py:281-283).
 
-`--score all_kmers` goes to kmerpapa_b200.algorithms.all_kmers_CV.  Out of scope in this build:
---greedy, --greedyCV and --BayesOpt are accepted by the parser like in the reference but stop with a clear error.
+`--score all_kmers` goes to kmerpapa_b200.algorithms.all_kmers_CV, `--greedy` / `--greedyCV` to
+kmerpapa_b200.algorithms.greedy_penalty_plus_pseudo.  --BayesOpt (scikit-optimize) is accepted by the parser like in
+the reference but stops with a clear error.
 """
 import argparse
 import sys
@@ -37,9 +38,9 @@ def get_parser():
                    help="File with the held-out likelihood of every (pseudo count, penalty) pair tried.")
     p.add_argument("--verbosity", type=int, default=1, help="0: silent, 1: default, 2: verbose (stderr)")
     p.add_argument("--CV_only", action="store_true", help="Only run cross validation, no final fit.")
-    p.add_argument("--greedy", action="store_true", help="(reference heuristic; not part of this build)")
+    p.add_argument("--greedy", action="store_true", help="Use the greedy (top-down) partition instead of the optimal one.")
     p.add_argument("--BayesOpt", action="store_true", help="(reference heuristic; not part of this build)")
-    p.add_argument("--greedyCV", action="store_true", help="(reference heuristic; not part of this build)")
+    p.add_argument("--greedyCV", action="store_true", help="Cross validate with the greedy partition, then fit the optimal one.")
     p.add_argument("-l", "--long_output", action="store_true", help="Print one row per k-mer instead of one per pattern.")
     p.add_argument("-s", "--super_pattern", type=str,
                    help="Only k-mers matching this IUPAC pattern are used, e.g. NNANN when the positive file only "
@@ -137,9 +138,9 @@ def main(args=None):
         return 0
     if args.verbosity > 0:
         print(f"Input data read. {n_mut} positive k-mers and {n_unmut} negative k-mers", file=sys.stderr)
-    if args.greedy or args.greedyCV or args.BayesOpt:
-        raise SystemExit("kmerpapa_b200 implements the optimal pattern partition (and the all-k-mers model): --greedy, "
-                         "--greedyCV and --BayesOpt belong to the reference's greedy estimator and are not part of this build")
+    if args.BayesOpt:
+        raise SystemExit("--BayesOpt needs scikit-optimize (skopt), which is not part of this build; "
+                         "use the grid search (--greedyCV / --penalty_values / --pseudo_counts)")
     if args.penalty_values is not None:
         assert args.score == "penalty_and_pseudo", \
             f"you cannot specify penalty values when using the {args.score} score function"
@@ -157,7 +158,8 @@ def main(args=None):
     if args.CVfile is not None:
         print("k alpha P LL_test", file=args.CVfile)
 
-    from .algorithms import all_kmers_CV, bottum_up_array_penalty_plus_pseudo_CV, bottum_up_array_w_numba
+    from .algorithms import (all_kmers_CV, bottum_up_array_penalty_plus_pseudo_CV, bottum_up_array_w_numba,
+                             greedy_penalty_plus_pseudo)
 
     best_alpha = best_penalty = best_k = None
     ks = range(len(gen_pat), 1, -2) if args.test_smaller_k else [len(gen_pat)]
@@ -171,7 +173,12 @@ def main(args=None):
                 print(f"Running {args.nfolds}-fold cross validation on {k}-mers", file=sys.stderr)
             if k != len(this_gen_pat):
                 this_contextD, this_gen_pat = downsize_contextD(this_contextD, this_gen_pat, k)
-            if args.score == "all_kmers":
+            if args.greedy or args.greedyCV:   # grid search with the greedy partition (cli.py:217-225 of the reference)
+                assert args.score != "all_kmers", "greedy option cannot be used wil all-kmers"
+                CV = greedy_penalty_plus_pseudo.GridSearchCV(gen_pat, contextD, args.penalty_values, args.pseudo_counts,
+                                                             args.nfolds, args.iterations, args.seed)
+                this_alpha, this_penalty, test_score = CV.get_best_a_c()
+            elif args.score == "all_kmers":
                 this_alpha, test_score = all_kmers_CV.all_kmers(this_gen_pat, this_contextD, args.pseudo_counts, args,
                                                                 n_mut, n_unmut)
                 this_penalty = None
@@ -207,6 +214,10 @@ def main(args=None):
     if args.score == "all_kmers":   # every k-mer is its own pattern (cli.py:267-272 of the reference)
         best_score, M, U, names = 0, n_mut, n_unmut, list(iupac.matches(gen_pat))
         counts = [tuple(contextD[k][:2]) for k in names]
+    elif args.greedy:
+        best_score, M, U, names = greedy_penalty_plus_pseudo.greedy_partition(gen_pat, contextD, best_alpha, best_beta,
+                                                                              best_penalty, args)
+        counts = _pattern_counts(gen_pat, contextD, names)
     else:
         best_score, M, U, names = bottum_up_array_w_numba.pattern_partition_bottom_up(
             gen_pat, contextD, best_alpha, best_beta, best_penalty, args, n_mut, n_unmut)

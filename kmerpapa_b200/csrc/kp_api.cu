@@ -852,6 +852,65 @@ int kp_shard_gather(kp_shard *s, const uint64_t *h_patnums, uint64_t n, float *h
     return 0;
 }
 
+// float64 sum of the leaves' losses in the order of the recursion (s1 + s2 at every inner node; keys sorted ascending)
+static double tree_sum_f64(const KpGreedyLeaf *lv, size_t lo, size_t hi, int depth)
+{
+    if (hi - lo == 1) return lv[lo].loss;
+    const unsigned long long bit = 1ULL << (63 - depth);
+    size_t a = lo, b = hi;
+    while (a < b) {
+        size_t mid = (a + b) / 2;
+        if (lv[mid].key & bit) b = mid; else a = mid + 1;
+    }
+    if (a == lo || a == hi) return tree_sum_f64(lv, lo, hi, depth + 1);
+    volatile double l = tree_sum_f64(lv, lo, a, depth + 1), r = tree_sum_f64(lv, a, hi, depth + 1);
+    volatile double sum = l + r;
+    return sum;
+}
+
+uint64_t kp_greedy_ws_bytes(uint64_t cap) { return 2 * cap * sizeof(KpBtNode) + 2 * cap * sizeof(KpGreedyLeaf) + 80 * 8 + 64; }
+
+int kp_greedy(kp_plan *p, const int64_t *d_kmerM, const int64_t *d_kmerU, const int64_t *d_testM, const int64_t *d_testU,
+              double alpha, double beta, double penalty, void *d_ws, uint64_t cap, uint64_t *h_patnums, double *h_loss,
+              double *h_test, uint64_t *n_out, double *h_total, void *stream)
+{
+    if (!p || !d_kmerM || !d_kmerU || !d_ws || !h_patnums || !n_out) return fail("kp_greedy: null argument");
+    if ((d_testM == nullptr) != (d_testU == nullptr)) return fail("kp_greedy: give both held-out tables or none");
+    if (p->host.t.total_level > 63) return fail("kp_greedy: more than 63 levels");
+    cudaStream_t st = (cudaStream_t)stream;
+    KP_CUDA(cudaSetDevice(p->device));
+    KpBtNode *fa = (KpBtNode *)d_ws, *fb = fa + cap;
+    KpGreedyLeaf *leaves = (KpGreedyLeaf *)(fb + cap), *sorted = leaves + cap;
+    unsigned long long *ctr = (unsigned long long *)(sorted + cap);
+    kp_backtrack_init_kernel<<<1, 128, 0, st>>>(fa, p->host.npat - 1, ctr);
+    const int levels = (int)p->host.t.total_level + 1;
+    int grid = cap < (uint64_t)p->sm_count * 4 ? (int)cap : p->sm_count * 4;
+    for (int d = 0; d < levels && d < 64; d++) {
+        kp_greedy_level_kernel<<<grid, 256, 0, st>>>(p->d_tab, (const long long *)d_kmerM, (const long long *)d_kmerU,
+                                                     (const long long *)d_testM, (const long long *)d_testU, alpha, beta, penalty, d,
+                                                     (d & 1) ? fb : fa, (d & 1) ? fa : fb, leaves, cap, ctr);
+        p->launches++;
+    }
+    kp_greedy_sort_kernel<<<p->sm_count, 256, 0, st>>>(leaves, ctr, cap, sorted);
+    p->launches += 2;
+    KP_CUDA(cudaGetLastError());
+    unsigned long long hc[2] = {0, 0};
+    KP_CUDA(cudaMemcpyAsync(hc, ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    *n_out = hc[0];
+    if (hc[1] || hc[0] > cap || hc[0] == 0) return fail("kp_greedy: partition larger than the workspace capacity");
+    std::vector<KpGreedyLeaf> hv(hc[0]);
+    KP_CUDA(cudaMemcpyAsync(hv.data(), sorted, hc[0] * sizeof(KpGreedyLeaf), cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < hv.size(); i++) {
+        h_patnums[i] = hv[i].pat;
+        if (h_loss) h_loss[i] = hv[i].loss;
+        if (h_test) h_test[i] = hv[i].test;
+    }
+    if (h_total) *h_total = tree_sum_f64(hv.data(), 0, hv.size(), 0);
+    return 0;
+}
+
 int kp_kmer_fold_terms(int device, const int64_t *h_Mtr, const int64_t *h_Utr, const int64_t *h_Mte, const int64_t *h_Ute,
                        const double *h_beta, uint64_t n, double alpha, double *h_train, double *h_test)
 {

@@ -328,6 +328,20 @@ def make_cli(which):
         argv = ["-p", f"{d}/mutated_5mers.txt", "-b", f"{d}/background_5mers.txt", "--score", "all_kmers",
                 "-a", "0.5", "1", "10", "--nfolds", "3", "--seed", "2"]
         run_worker("cli", {"argv": argv, "cvfile": False}, os.path.join(HERE, "cli_5mers_all_kmers.json"))
+    elif which == "cli5_greedy":     # the greedy (top-down) partition as the final fit
+        argv = ["-p", f"{d}/mutated_5mers.txt", "-b", f"{d}/background_5mers.txt", "-c", "5", "-a", "0.8", "--greedy"]
+        run_worker("cli", {"argv": argv, "cvfile": False}, os.path.join(HERE, "cli_5mers_greedy.json"))
+    elif which == "cli5_greedycv":   # grid-search CV with the greedy partition, final fit with the optimal DP
+        argv = ["-p", f"{d}/mutated_5mers.txt", "-b", f"{d}/background_5mers.txt", "-c", "3", "5", "-a", "0.5", "1",
+                "--greedyCV", "--seed", "1"]
+        run_worker("cli", {"argv": argv, "cvfile": False}, os.path.join(HERE, "cli_5mers_greedyCV.json"))
+    elif which == "cli5_greedy_both":  # greedy CV (3 folds, 2 repeats) and greedy final fit
+        argv = ["-p", f"{d}/mutated_5mers.txt", "-b", f"{d}/background_5mers.txt", "-c", "3", "6", "-a", "0.5", "2",
+                "--greedy", "--nfolds", "3", "--iterations", "2", "--seed", "4"]
+        run_worker("cli", {"argv": argv, "cvfile": False}, os.path.join(HERE, "cli_5mers_greedy_cv_and_fit.json"))
+    elif which == "cli7_greedy":     # greedy final fit on the 7-mers
+        argv = ["-p", f"{d}/mutated_7mers.txt", "-b", f"{d}/background_7mers.txt", "-c", "6", "-a", "10", "--greedy"]
+        run_worker("cli", {"argv": argv, "cvfile": False}, os.path.join(HERE, "cli_7mers_greedy.json"))
     elif which == "cli5_scores":   # the information-criterion penalties (--score BIC)
         argv = ["-p", f"{d}/mutated_5mers.txt", "-b", f"{d}/background_5mers.txt", "--score", "BIC", "-a", "1"]
         run_worker("cli", {"argv": argv, "cvfile": False}, os.path.join(HERE, "cli_5mers_BIC.json"))
@@ -362,7 +376,7 @@ def main():
             make_small()
         if w == "all":
             for c in ("cli5", "cli5_single", "cli5_sp", "cli5_negative", "cli5_joint", "cli5_trim", "cli5_smallerk",
-                      "cli5_iter2", "cli5_verbose", "cli5_allkmers", "cli5_scores", "cli7_single", "cli7"):
+                      "cli5_iter2", "cli5_verbose", "cli5_allkmers", "cli5_greedy", "cli5_greedycv", "cli5_greedy_both", "cli7_greedy", "cli5_scores", "cli7_single", "cli7"):
                 make_cli(c)
         elif w.startswith("cli"):
             make_cli(w)

@@ -31,7 +31,8 @@ def _run(golden_name, tmp_path):
 
 @pytest.mark.parametrize("name", ["cli_cfg1_5mers.json", "cli_5mers_single.json", "cli_5mers_superpattern.json",
                                   "cli_5mers_negative.json", "cli_5mers_joint.json", "cli_5mers_trimmed_background.json",
-                                  "cli_5mers_smaller_k.json", "cli_5mers_BIC.json", "cli_5mers_iterations2.json", "cli_5mers_verbose.json", "cli_5mers_all_kmers.json",
+                                  "cli_5mers_smaller_k.json", "cli_5mers_BIC.json", "cli_5mers_iterations2.json", "cli_5mers_verbose.json", "cli_5mers_all_kmers.json", "cli_5mers_greedy.json", "cli_5mers_greedyCV.json",
+                                  "cli_5mers_greedy_cv_and_fit.json", "cli_7mers_greedy.json",
                                   "cli_7mers_single.json", "cli_cfg2_7mers.json"])
 def test_cli_output_identical_to_reference(name, tmp_path):
     g, rc, out, cv, lines, ref_lines = _run(name, tmp_path)
