@@ -216,3 +216,75 @@ def cv_grid(gen_pat, kmerM, kmerU, alphas, penalties, nfolds, seed, nthreads=0, 
             if test < best:
                 best_vals, best = (alpha, penalty), test
     return {"rows": rows, "best": (best_vals[0], best_vals[1], best), "per_job": per_job, "folds": (Mf, Uf)}
+
+
+# ---------------------------------------------------------------------------------------------
+# Greedy (top-down) partition: restatement of the reference's
+# src/kmerpapa/algorithms/greedy_penalty_plus_pseudo.py:17-35 (train_loss, test_logLik) and :155-196
+# (greedy_res_kmer_table_ord) in plain Python floats (math.log is the libm log numba calls).
+# ---------------------------------------------------------------------------------------------
+COMPLEMENTS = {"R": [("A", "G")], "Y": [("C", "T")], "S": [("G", "C")], "W": [("A", "T")], "K": [("G", "T")], "M": [("A", "C")],
+               "V": [("A", "S"), ("C", "R"), ("G", "M")], "H": [("A", "Y"), ("C", "W"), ("T", "M")],
+               "D": [("A", "K"), ("G", "W"), ("T", "R")], "B": [("C", "K"), ("G", "Y"), ("T", "S")],
+               "N": [("S", "W"), ("K", "M"), ("R", "Y"), ("A", "B"), ("C", "D"), ("G", "H"), ("T", "V")]}
+
+
+def _greedy_loss(M, U, alpha, beta, penalty):
+    import math
+
+    M, U = float(M), float(U)
+    p = (M + alpha) / (M + U + alpha + beta)
+    s = penalty
+    if M > 0:
+        s += -2.0 * M * math.log(p)
+    if U > 0:
+        s += -2.0 * U * math.log(1 - p)
+    return s
+
+
+def _greedy_test_ll(M, U, Mt, Ut, alpha, beta):
+    import math
+
+    M, U, Mt, Ut = float(M), float(U), float(Mt), float(Ut)
+    p = (M + alpha) / (M + U + alpha + beta)
+    s = 0.0
+    if Mt > 0:
+        s += -2.0 * Mt * math.log(p)
+    if Ut > 0:
+        s += -2.0 * Ut * math.log(1 - p)
+    return s
+
+
+def greedy(gen_pat, kmerM, kmerU, alpha, beta, penalty, testM=None, testU=None):
+    """Returns (score, [patterns in the reference's order], [loss per pattern], [held-out LL per pattern] or None).
+    kmerM/kmerU (and the held-out tables): counts in k-mer index order (kmers_of)."""
+    index = {k: i for i, k in enumerate(kmers_of(gen_pat))}
+
+    def counts(pattern, tabs):
+        ks = [index[k] for k in kmers_of(pattern)]
+        return [sum(int(t[i]) for i in ks) for t in tabs]
+
+    tabs = [kmerM, kmerU] + ([testM, testU] if testM is not None else [])
+
+    def rec(pattern):
+        c = counts(pattern, tabs)
+        best = _greedy_loss(c[0], c[1], alpha, beta, penalty)
+        mine = (best, [pattern], [best], [_greedy_test_ll(c[0], c[1], c[2], c[3], alpha, beta)] if testM is not None else None)
+        if all(ch in "ACGT" for ch in pattern):
+            return mine
+        choice = None
+        for i, ch in enumerate(pattern):
+            for c1, c2 in COMPLEMENTS.get(ch, []):
+                p1, p2 = pattern[:i] + c1 + pattern[i + 1:], pattern[:i] + c2 + pattern[i + 1:]
+                a, b = counts(p1, tabs[:2]), counts(p2, tabs[:2])
+                s = _greedy_loss(a[0], a[1], alpha, beta, penalty) + _greedy_loss(b[0], b[1], alpha, beta, penalty)
+                if s < best:
+                    best, choice = s, (p1, p2)
+        if choice is None:
+            return mine
+        s1, n1, l1, t1 = rec(choice[0])
+        s2, n2, l2, t2 = rec(choice[1])
+        return s1 + s2, n1 + n2, l1 + l2, (t1 + t2 if testM is not None else None)
+
+    return rec(gen_pat)
+

@@ -251,3 +251,34 @@ def test_pack_counts_sums_duplicates_and_rejects_bad_codes(eng):
     assert hM[idx] == idx + len(kmers)
     with pytest.raises(KpError):
         plan.pack_counts(np.array([iupac.kmer_code("CCG")], dtype=np.uint64), np.ones(1, np.int64), np.ones(1, np.int64))
+
+
+@pytest.mark.parametrize("gen_pat,seed", [("NNN", 1), ("NNMNN", 2), ("RYNAN", 3), ("BDHV", 4), ("NNNNN", 5), ("SWKMN", 6),
+                                          ("A", 7), ("NTNBN", 8)])
+def test_greedy_against_oracle(eng, oracle, gen_pat, seed):
+    """kp_greedy (one launch per depth, one CTA per pattern) against the plain-Python restatement of the reference's
+    greedy recursion: same leaves in the same order, float64 losses / held-out LLs / score bit for bit."""
+    from kmerpapa_b200 import iupac
+    from kmerpapa_b200.algorithms import greedy_penalty_plus_pseudo as gr
+
+    rng = np.random.default_rng(seed)
+    km = oracle.kmers_of(gen_pat)
+    U = rng.integers(0, 4000, size=len(km)) * (rng.random(len(km)) < 0.9)
+    M = rng.binomial(np.maximum(U, 1), 0.03)
+    if M.sum() == 0:
+        M[0] = 3
+    Mt, Ut = rng.binomial(M, 0.3), rng.binomial(U, 0.3)
+    plan = eng.get_plan(gen_pat)
+    PE = iupac.PatternEnumeration(gen_pat)
+    for alpha, pen in ((0.8, 4.0), (10.0, 0.5), (1.0, 30.0)):
+        mu = M.sum() / (M.sum() + U.sum())
+        beta = (alpha * (1.0 - mu)) / mu
+        kM, kU = plan.upload_kmer_tables(M - Mt, U - Ut, name="g_tr")
+        tM, tU = plan.upload_kmer_tables(Mt, Ut, name="g_te")
+        pats, loss, tst, score = gr._greedy(plan, kM, kU, alpha, beta, pen, test=(tM, tU))
+        rscore, rnames, rloss, rtest = oracle.greedy(gen_pat, M - Mt, U - Ut, alpha, beta, pen, Mt, Ut)
+        assert [PE.num2pattern(p) for p in pats] == rnames
+        assert np.array_equal(loss.view(np.uint64), np.array(rloss, dtype=np.float64).view(np.uint64))
+        assert np.array_equal(tst.view(np.uint64), np.array(rtest, dtype=np.float64).view(np.uint64))
+        assert np.float64(score).tobytes() == np.float64(rscore).tobytes()
+

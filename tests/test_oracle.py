@@ -114,3 +114,29 @@ def test_cv_full_table_one_fold(oracle):
         train, test = oracle.cv_job(gp, Mtot, Utot, Mf[:, f], Uf[:, f], alphas[a_i], betas[f], pens[p_i])
         assert np.array_equal(_bits(train), _bits(g["train_tables"][-1][:, f]))
         assert np.array_equal(_bits(test), _bits(g["last_test_table"][:, f]))
+
+
+def test_greedy_restatement_matches_reference_cli(oracle):
+    """oracle.greedy (plain-Python restatement of greedy_res_kmer_table_ord) against the recorded reference run
+    `--greedy -c 5 -a 0.8` on the 5-mer test data: same patterns in the same order, same float64 loss text."""
+    import json
+    import os
+
+    from conftest import GOLDEN
+
+    g = json.load(open(os.path.join(GOLDEN, "cli_5mers_greedy.json")))
+    pos, bg = {}, {}
+    for name, tab in (("mutated_5mers.txt", pos), ("background_5mers.txt", bg)):
+        for line in open(os.path.join(GOLDEN, "data", name)):
+            k, c = line.split()
+            tab[k] = tab.get(k, 0) + int(c)
+    gp = "NNMNN"
+    km = oracle.kmers_of(gp)
+    M = [pos.get(k, 0) for k in km]
+    U = [bg.get(k, 0) - pos.get(k, 0) for k in km]
+    alpha, pen = 0.8, 5.0
+    mu = sum(M) / (sum(M) + sum(U))
+    score, names, _, _ = oracle.greedy(gp, M, U, alpha, (alpha * (1.0 - mu)) / mu, pen)
+    assert names == [line.split()[0] for line in g["stdout"].splitlines()[1:]]
+    assert f"loss={score}" in g["stderr"]
+
