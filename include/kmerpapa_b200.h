@@ -69,6 +69,10 @@ int kp_version(void);
 
 /* gen_pat: IUPAC general pattern, e.g. "NNNNANNNN".  device: CUDA ordinal. */
 int kp_plan_create(const char *gen_pat, int device, kp_plan **out);
+/* A plan WITHOUT the DP's tile lattice: digit and k-mer tables only, for the entry points that work on the k-mer tables
+ * (kp_pack_counts, kp_pattern_counts, kp_greedy).  Any general pattern whose k-mer table fits the device is accepted;
+ * kp_expand_counts, the DP, the backtrack and the shard functions refuse such a plan. */
+int kp_plan_create_lite(const char *gen_pat, int device, kp_plan **plan);
 int kp_plan_destroy(kp_plan *plan);
 int kp_plan_get_info(const kp_plan *plan, kp_plan_info *out);
 

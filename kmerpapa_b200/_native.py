@@ -39,6 +39,7 @@ SYMBOLS = {
     "kp_last_error": (_cp, []),
     "kp_version": (_int, []),
     "kp_plan_create": (_int, [_cp, _int, ctypes.POINTER(_vp)]),
+    "kp_plan_create_lite": (_int, [_cp, _int, ctypes.POINTER(_vp)]),
     "kp_plan_destroy": (_int, [_vp]),
     "kp_plan_get_info": (_int, [_vp, ctypes.POINTER(PlanInfo)]),
     "kp_pack_counts": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp]),

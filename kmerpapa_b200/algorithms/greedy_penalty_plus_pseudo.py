@@ -53,7 +53,7 @@ def greedy_partition(genpat, contextD, alpha, beta, penalty, args):
     kmers, table = _kmer_table(genpat, contextD)
     MU = table.sum(axis=0)
     beta = get_betas(alpha, MU[0], MU[1])
-    plan = get_plan(genpat)
+    plan = get_plan(genpat, lite=True)
     kM, kU = plan.upload_kmer_tables(table[:, 0], table[:, 1], name="greedy_k")
     pats, _, _, score = _greedy(plan, kM, kU, alpha, beta, penalty)
     PE = iupac.PatternEnumeration(genpat)
@@ -66,7 +66,7 @@ class CrossValidation:
         _, self.kmer_table = _kmer_table(genpat, contextD)
         prng = np.random.RandomState(seed)
         self.fold_kmer_table = CV_tools.make_all_folds(self.kmer_table, nfolds, nit, prng)
-        self.plan = get_plan(genpat)
+        self.plan = get_plan(genpat, lite=True)
 
     def loglik(self, alpha, penalty):
         """Mean over the repeats of the summed held-out -2 log-likelihood of the greedy partitions of the train folds."""

@@ -84,7 +84,7 @@ def _pattern_counts(gen_pat, contextD, names):
     from .algorithms.bottum_up_array_w_numba import kmer_arrays
     from .engine import get_plan
 
-    plan = get_plan(gen_pat)
+    plan = get_plan(gen_pat, lite=True)
     codes, pos, neg = kmer_arrays(contextD)
     kM, kU = plan.pack_counts(codes, pos, neg, name="out_k")
     PE = iupac.PatternEnumeration(gen_pat)

@@ -122,7 +122,13 @@ static const void *dp_kernel_ptr(int r0, int rp, bool wide)
     return wide ? dp_kernel_for_radix<true>(r0, rp) : dp_kernel_for_radix<false>(r0, rp);
 }
 
-int kp_plan_create(const char *gen_pat, int device, kp_plan **out)
+static int plan_create(const char *gen_pat, int device, bool lattice, kp_plan **out);
+
+int kp_plan_create(const char *gen_pat, int device, kp_plan **out) { return plan_create(gen_pat, device, true, out); }
+
+int kp_plan_create_lite(const char *gen_pat, int device, kp_plan **out) { return plan_create(gen_pat, device, false, out); }
+
+static int plan_create(const char *gen_pat, int device, bool lattice, kp_plan **out)
 {
     if (!gen_pat || !out) return fail("kp_plan_create: null argument");
     int ndev = 0;
@@ -133,7 +139,7 @@ int kp_plan_create(const char *gen_pat, int device, kp_plan **out)
     KP_CUDA(cudaSetDevice(device));
     kp_plan *p = new kp_plan();
     std::string err;
-    if (kp_build_host_plan(gen_pat, p->host, err)) { delete p; return fail("kp_plan_create: " + err); }
+    if (kp_build_host_plan(gen_pat, p->host, err, lattice)) { delete p; return fail("kp_plan_create: " + err); }
     p->device = device;
     cudaDeviceProp prop;
     KP_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -143,14 +149,14 @@ int kp_plan_create(const char *gen_pat, int device, kp_plan **out)
     KP_CUDA(cudaMemcpy(p->d_tab, &t, sizeof(KpTables), cudaMemcpyHostToDevice));
     KP_CUDA(cudaMalloc(&p->d_rowtab, p->host.rowtab.size()));
     KP_CUDA(cudaMemcpy(p->d_rowtab, p->host.rowtab.data(), p->host.rowtab.size(), cudaMemcpyHostToDevice));
-    KP_CUDA(cudaMalloc(&p->d_tiles, sizeof(uint32_t) * p->host.tile_order.size()));
+    KP_CUDA(cudaMalloc(&p->d_tiles, sizeof(uint32_t) * (p->host.tile_order.size() + 1)));
     KP_CUDA(cudaMemcpy(p->d_tiles, p->host.tile_order.data(), sizeof(uint32_t) * p->host.tile_order.size(), cudaMemcpyHostToDevice));
     KP_CUDA(cudaMalloc(&p->d_genmask, KP_MAXK));
     KP_CUDA(cudaMemcpy(p->d_genmask, p->host.gen_mask, KP_MAXK, cudaMemcpyHostToDevice));
     KP_CUDA(cudaMalloc(&p->d_err, sizeof(int)));
     KP_CUDA(cudaMemset(p->d_err, 0, sizeof(int)));
     KP_CUDA(cudaMalloc(&p->d_counters, sizeof(uint32_t) * 128));
-    if (t.r0 == 15 && t.nhigh > 0) {
+    if (t.r0 == 15 && t.nhigh > 0 && lattice) {
         std::vector<uint8_t> tw(p->host.tile_order.size());
         for (size_t l = 0; l + 1 < p->host.hl_off.size(); l++)
             for (uint64_t i = p->host.hl_off[l]; i < p->host.hl_off[l + 1]; i++) tw[i] = (uint8_t)l;
@@ -225,6 +231,7 @@ uint64_t kp_plan_launch_count(const kp_plan *p) { return p ? p->launches : 0; }
 
 int kp_pattern_offset(const kp_plan *p, uint64_t patnum, uint64_t *table_elem, uint64_t *kept_elem, uint32_t *kept_bit)
 {
+    if (p && !p->host.lattice) return fail("kp_pattern_offset: this plan was created without the tile lattice (kp_plan_create_lite)");
     if (!p) return fail("kp_pattern_offset: null plan");
     if (patnum >= p->host.npat) return fail("kp_pattern_offset: pattern number out of range");
     uint64_t tile; uint32_t srow, d0;
@@ -291,6 +298,7 @@ int kp_expand_counts(kp_plan *p, const int64_t *d_kmerM, const int64_t *d_kmerU,
                      void *stream)
 {
     if (!p) return fail("kp_expand_counts: null plan");
+    if (!p->host.lattice) return fail("kp_expand_counts: this plan was created without the tile lattice (kp_plan_create_lite)");
     cudaStream_t st = (cudaStream_t)stream;
     KP_CUDA(cudaSetDevice(p->device));
     const KpTables &t = p->host.t;
@@ -314,6 +322,7 @@ int kp_expand_counts(kp_plan *p, const int64_t *d_kmerM, const int64_t *d_kmerU,
 
 static int launch_dp(kp_plan *p, bool wide, KpDpParams prm, cudaStream_t st)
 {
+    if (!p->host.lattice) return fail("this plan was created without the tile lattice (kp_plan_create_lite): no DP");
     int nw = p->nwarps[wide];
     if (nw < 1) return fail("DP kernel does not fit in shared memory for this tile shape");
     size_t nhl = p->host.hl_off.size() - 1;
@@ -627,6 +636,7 @@ int kp_shard_assignment(const kp_plan *p, int world, uint8_t *owner16, uint8_t *
 int kp_shard_create(kp_plan *p, int rank, int world, int replicate, kp_shard **out)
 {
     if (!p || !out) return fail("kp_shard_create: null argument");
+    if (!p->host.lattice) return fail("kp_shard_create: this plan was created without the tile lattice (kp_plan_create_lite)");
     const KpTables &t = p->host.t;
     if (t.r0 != 15) return fail("kp_shard_create: the sharded DP needs an N position in the general pattern");
     if (rank < 0 || rank >= world) return fail("kp_shard_create: bad rank");

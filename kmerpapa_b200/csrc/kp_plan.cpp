@@ -53,8 +53,9 @@ const uint8_t kDigitBases15[15] = {1, 2, 4, 8, 5, 10, 6, 9, 12, 3, 14, 13, 11, 7
 
 }  // namespace
 
-int kp_build_host_plan(const char *gen_pat, KpHostPlan &P, std::string &err)
+int kp_build_host_plan(const char *gen_pat, KpHostPlan &P, std::string &err, bool lattice)
 {
+    P.lattice = lattice;
     size_t len = strlen(gen_pat);
     if (len < 1 || len > KP_MAXK) { err = "general pattern length must be 1.." + std::to_string(KP_MAXK); return 1; }
     P.gen = gen_pat;
@@ -145,7 +146,10 @@ int kp_build_host_plan(const char *gen_pat, KpHostPlan &P, std::string &err)
         } else {
             t.highpos[t.nhigh++] = (uint8_t)e;
             t.highw[e] = hw;
-            if ((uint64_t)hw * t.radix[e] >= (1ull << 31)) { err = "too many tiles"; return 6; }
+            if ((uint64_t)hw * t.radix[e] >= (1ull << 31)) {
+                if (lattice) { err = "too many tiles"; return 6; }
+                hw = 0;   // no lattice: the tile weights are never used
+            }
             hw *= t.radix[e];
         }
     }
@@ -284,6 +288,11 @@ int kp_build_host_plan(const char *gen_pat, KpHostPlan &P, std::string &err)
         t.warp_smem_bytes[wide] = (uint32_t)((b + 15) & ~(size_t)15);
     }
 
+    if (!lattice) {
+        t.ntiles = 0;
+        P.hl_off.assign(1, 0);
+        return 0;
+    }
     // ---- tiles sorted by high level ----
     int nhl = 1;
     for (int i = 0; i < t.nhigh; i++) nhl += t.nbase[t.highpos[i]] - 1;

@@ -18,10 +18,12 @@ struct KpHostPlan {
     std::vector<uint64_t> hl_off;      // offsets of the high levels in tile_order (size nhl + 1)
     uint8_t gen_mask[KP_MAXK];         // nucleotide subset of every string position (fixed ones too)
     uint8_t eff_of_pos[KP_MAXK];       // string position -> effective position index, 0xFF if fixed
+    bool lattice = true;               // false: no tile lattice (tile_order / hl_off empty, the DP entry points refuse)
 };
 
 // Returns 0 on success; on failure fills err.
-int kp_build_host_plan(const char *gen_pat, KpHostPlan &P, std::string &err);
+// lattice = false: digit / k-mer tables only (greedy estimator, counts); no tile lattice, so any k the k-mer table allows
+int kp_build_host_plan(const char *gen_pat, KpHostPlan &P, std::string &err, bool lattice = true);
 
 // dense pattern number -> (tile, row in schedule order, digit of the register position)
 void kp_locate(const KpHostPlan &P, uint64_t pat, uint64_t *tile, uint32_t *srow, uint32_t *d0);

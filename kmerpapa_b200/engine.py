@@ -24,23 +24,28 @@ def _torch():
 class PartitionPlan:
     """Tables, launch geometry and reusable device buffers for one general pattern on one GPU."""
 
-    def __init__(self, gen_pat, device=None):
+    def __init__(self, gen_pat, device=None, lite=False):
+        """lite=True: no tile lattice (k-mer tables only: pack_counts, pattern_counts, the greedy estimator)."""
         torch = _torch()
+        self.lite = bool(lite)
         self.lib = _native.lib()
         self.gen_pat = gen_pat
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", self.device_index)
         h = ctypes.c_void_p()
-        check(self.lib.kp_plan_create(gen_pat.encode(), self.device_index, ctypes.byref(h)), "kp_plan_create")
+        create = self.lib.kp_plan_create_lite if self.lite else self.lib.kp_plan_create
+        check(create(gen_pat.encode(), self.device_index, ctypes.byref(h)), "kp_plan_create")
         self.handle = h
         info = _native.PlanInfo()
         check(self.lib.kp_plan_get_info(h, ctypes.byref(info)), "kp_plan_get_info")
         self.info = info
         self.npat, self.nkmer = int(info.npat), int(info.nkmer)
         self._buf = {}
-        off = ctypes.c_uint64()
-        check(self.lib.kp_pattern_offset(h, self.npat - 1, ctypes.byref(off), None, None), "kp_pattern_offset")
-        self.top_elem = int(off.value)
+        self.top_elem = None
+        if not self.lite:
+            off = ctypes.c_uint64()
+            check(self.lib.kp_pattern_offset(h, self.npat - 1, ctypes.byref(off), None, None), "kp_pattern_offset")
+            self.top_elem = int(off.value)
 
     def __del__(self):
         try:
@@ -218,15 +223,17 @@ class PartitionPlan:
         return out
 
 
-def get_plan(gen_pat, device=None):
-    """Cached PartitionPlan per (general pattern, device)."""
+def get_plan(gen_pat, device=None, lite=False):
+    """Cached PartitionPlan per (general pattern, device).  lite=True accepts a full plan too (it can do everything a
+    lattice-free plan can) and otherwise builds one without the DP's tile lattice."""
     torch = _torch()
     dev = torch.cuda.current_device() if device is None else int(device)
-    key = (gen_pat, dev)
-    plan = _PLANS.get(key)
+    plan = _PLANS.get((gen_pat, dev, False))
+    if plan is None and lite:
+        plan = _PLANS.get((gen_pat, dev, True))
     if plan is None:
-        plan = PartitionPlan(gen_pat, dev)
-        _PLANS[key] = plan
+        plan = PartitionPlan(gen_pat, dev, lite=lite)
+        _PLANS[(gen_pat, dev, bool(lite))] = plan
     return plan
 
 

@@ -282,3 +282,44 @@ def test_greedy_against_oracle(eng, oracle, gen_pat, seed):
         assert np.array_equal(tst.view(np.uint64), np.array(rtest, dtype=np.float64).view(np.uint64))
         assert np.float64(score).tobytes() == np.float64(rscore).tobytes()
 
+
+def test_lattice_free_plan(eng):
+    """kp_plan_create_lite: the greedy estimator and the count queries work without the DP's tile lattice (and so for
+    general patterns far beyond the DP's reach); the DP entry points refuse such a plan."""
+    from kmerpapa_b200 import iupac, synthetic
+    from kmerpapa_b200._native import KpError
+    from kmerpapa_b200.algorithms import greedy_penalty_plus_pseudo as gr
+    from kmerpapa_b200.engine import PartitionPlan
+
+    gen_pat = "NNNANNN"
+    kmers, pos, neg = synthetic.negbin_counts(gen_pat, 5)
+    mu = pos.sum() / (pos.sum() + neg.sum())
+    full, lite = eng.get_plan(gen_pat), PartitionPlan(gen_pat, 0, lite=True)
+    res = []
+    for plan in (full, lite):
+        kM, kU = plan.upload_kmer_tables(pos, neg, name="lf")
+        res.append(gr._greedy(plan, kM, kU, 1.0, (1 - mu) / mu, 5.0))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and res[0][3] == res[1][3]
+    M, U = lite.pattern_counts(kM, kU, res[1][0])
+    assert M.sum() == pos.sum() and U.sum() == neg.sum()
+    with pytest.raises(KpError):
+        lite.expand(kM, kU)
+    # 12 free positions: 15^12 = 1.3e14 patterns, no DP table could hold them; the greedy needs the 4^10 k-mers only
+    big = "NNNNNANNNNN"
+    plan = PartitionPlan(big, 0, lite=True)
+    assert plan.npat == 15 ** 10
+    rng = np.random.default_rng(3)
+    n = 4 ** 10
+    U = 1 + rng.negative_binomial(2, 2 / (2 + 2000.0), size=n)
+    first = np.arange(n) % 4
+    M = rng.binomial(U, 0.002 * (1 + first))     # the rate depends on the first position only
+    kM, kU = plan.upload_kmer_tables(M, U, name="lfbig")
+    mu = M.sum() / (M.sum() + U.sum())
+    pats, loss, _, score = gr._greedy(plan, kM, kU, 1.0, (1 - mu) / mu, 8.0)
+    PE = iupac.PatternEnumeration(big)
+    names = [PE.num2pattern(p) for p in pats]
+    assert sum(int(np.prod([len(iupac.CODE[c]) for c in nm])) for nm in names) == n      # a partition of the k-mers
+    Mp, Up = plan.pattern_counts(kM, kU, pats)
+    assert Mp.sum() == M.sum() and Up.sum() == U.sum()
+    assert all(nm[0] != "N" for nm in names) and len(names) < 200      # the signal sits in position 0: it is always split
+
