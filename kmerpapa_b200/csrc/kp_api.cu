@@ -878,7 +878,10 @@ static double tree_sum_f64(const KpGreedyLeaf *lv, size_t lo, size_t hi, int dep
     return sum;
 }
 
-uint64_t kp_greedy_ws_bytes(uint64_t cap) { return 2 * cap * sizeof(KpBtNode) + 2 * cap * sizeof(KpGreedyLeaf) + 80 * 8 + 64; }
+uint64_t kp_greedy_ws_bytes(uint64_t cap)
+{
+    return 2 * cap * sizeof(KpBtNode) + 2 * cap * sizeof(KpGreedyLeaf) + 80 * 8 + cap * KP_GREEDY_ACC * 8 + 2 * cap * 8 + 64;
+}
 
 int kp_greedy(kp_plan *p, const int64_t *d_kmerM, const int64_t *d_kmerU, const int64_t *d_testM, const int64_t *d_testU,
               double alpha, double beta, double penalty, void *d_ws, uint64_t cap, uint64_t *h_patnums, double *h_loss,
@@ -892,14 +895,22 @@ int kp_greedy(kp_plan *p, const int64_t *d_kmerM, const int64_t *d_kmerU, const 
     KpBtNode *fa = (KpBtNode *)d_ws, *fb = fa + cap;
     KpGreedyLeaf *leaves = (KpGreedyLeaf *)(fb + cap), *sorted = leaves + cap;
     unsigned long long *ctr = (unsigned long long *)(sorted + cap);
+    unsigned long long *acc = ctr + 80;
+    unsigned long long *sa = acc + cap * KP_GREEDY_ACC, *sb = sa + cap;   // k-mers per frontier node
     kp_backtrack_init_kernel<<<1, 128, 0, st>>>(fa, p->host.npat - 1, ctr);
+    kp_greedy_init_kernel<<<1, 1, 0, st>>>(sa, p->host.nkmer);
+    KP_CUDA(cudaMemsetAsync(acc, 0, cap * KP_GREEDY_ACC * 8, st));
     const int levels = (int)p->host.t.total_level + 1;
-    int grid = cap < (uint64_t)p->sm_count * 4 ? (int)cap : p->sm_count * 4;
+    const int grid = p->sm_count * 4;
+    const unsigned long long big = 32768;   // nodes with at least this many k-mers are shared by all CTAs
     for (int d = 0; d < levels && d < 64; d++) {
-        kp_greedy_level_kernel<<<grid, 256, 0, st>>>(p->d_tab, (const long long *)d_kmerM, (const long long *)d_kmerU,
-                                                     (const long long *)d_testM, (const long long *)d_testU, alpha, beta, penalty, d,
-                                                     (d & 1) ? fb : fa, (d & 1) ? fa : fb, leaves, cap, ctr);
-        p->launches++;
+        kp_greedy_marginals_kernel<<<grid, 256, 0, st>>>(p->d_tab, (const long long *)d_kmerM, (const long long *)d_kmerU,
+                                                         (const long long *)d_testM, (const long long *)d_testU, d,
+                                                         (d & 1) ? fb : fa, (d & 1) ? sb : sa, ctr, big, acc);
+        kp_greedy_decide_kernel<<<grid, 256, 0, st>>>(p->d_tab, d_testM != nullptr, alpha, beta, penalty, d, (d & 1) ? fb : fa,
+                                                      (d & 1) ? sb : sa, (d & 1) ? fa : fb, (d & 1) ? sa : sb, leaves, cap, ctr,
+                                                      acc);
+        p->launches += 2;
     }
     kp_greedy_sort_kernel<<<p->sm_count, 256, 0, st>>>(leaves, ctr, cap, sorted);
     p->launches += 2;

@@ -974,49 +974,50 @@ __global__ void kp_backtrack_sort_kernel(const KpBtNode *leaves, const unsigned 
 // A node is a pattern; its loss is the float64 self-score of its counts; among all two-way splits of one position
 // (scan order: string position, then split index) the first one whose float64 sum of the two children's losses is
 // the strict minimum below the node's own loss is taken, and both children are expanded in turn.
-// One launch per depth, one CTA per node: the CTA walks the node's k-mers once and accumulates, for every position
-// and base, the counts of the node restricted to that base (shared-memory atomics); every candidate child is a sum
-// of at most three of those marginals, so all candidates of the node are scored from one pass over its k-mers.
+// Two launches per depth.  The k-mers of a node are walked once, accumulating for every position and base the counts
+// of the node restricted to that base (shared-memory atomics, then global ones); every candidate child is a sum of
+// at most three of those marginals, so all candidates of the node are scored from that one pass.
 // ---------------------------------------------------------------------------------------------------
 struct KpGreedyLeaf { unsigned long long pat, key; double loss, test; };
 
-__global__ void __launch_bounds__(256) kp_greedy_level_kernel(const KpTables *tab, const long long *kmerM, const long long *kmerU,
-                                                              const long long *testM, const long long *testU, double alpha,
-                                                              double beta, double penalty, int depth, const KpBtNode *cur,
-                                                              KpBtNode *nxt, KpGreedyLeaf *leaves, unsigned long long cap,
-                                                              unsigned long long *ctr)
+// per-node accumulators in global memory: [position][base][M, U], then M, U, held-out M, held-out U of the node
+#define KP_GREEDY_ACC (KP_MAXPOS * 8 + 4)
+
+// Step 1 of a depth: marginal counts of every frontier node.  Small nodes: one CTA each.  Nodes with at least
+// `big` k-mers (the first few depths): every CTA takes a slice.  Shared-memory atomics per CTA, then one global
+// atomicAdd per non-zero counter.
+__global__ void __launch_bounds__(256) kp_greedy_marginals_kernel(const KpTables *tab, const long long *kmerM, const long long *kmerU,
+                                                                  const long long *testM, const long long *testU, int depth,
+                                                                  const KpBtNode *cur, const unsigned long long *cur_size,
+                                                                  const unsigned long long *ctr, unsigned long long big,
+                                                                  unsigned long long *acc)
 {
     const KpTables &tb = *tab;
-    __shared__ double2 logtab[128];
-    __shared__ unsigned long long marg[KP_MAXPOS][4][2];   // [position][base bit][M, U] of the node restricted to that base
-    __shared__ unsigned long long tot[4];                  // M, U, held-out M, held-out U of the node
-    __shared__ uint8_t s_mask[KP_MAXPOS];
-    __shared__ uint8_t s_bases[KP_MAXPOS][4];              // set bits of the mask, ascending
+    __shared__ unsigned long long marg[KP_GREEDY_ACC];
+    __shared__ uint8_t s_bases[KP_MAXPOS][4];
     __shared__ uint32_t s_n[KP_MAXPOS];
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) logtab[i] = make_double2(kpc_logTab[2 * i], kpc_logTab[2 * i + 1]);
-    const KpLogK K = kp_logk_load();
     const unsigned long long ncur = ctr[2 + depth];
     const int npos = tb.npos;
-    for (unsigned long long ni = blockIdx.x; ni < ncur; ni += gridDim.x) {
+    for (unsigned long long ni = 0; ni < ncur; ni++) {
+        const unsigned long long total = cur_size[ni];   // k-mers of the node
+        const bool shared_node = total >= big;
+        if (!shared_node && ni % gridDim.x != blockIdx.x) continue;
         const KpBtNode nd = cur[ni];
         __syncthreads();   // previous node's readers are done
         if (threadIdx.x < npos) {
             const int e = threadIdx.x;
-            const int d = (int)((nd.pat / tb.extw[e]) % tb.radix[e]);
-            const unsigned m = tb.digit_mask[e][d];
-            s_mask[e] = (uint8_t)m;
+            const unsigned m = tb.digit_mask[e][(int)((nd.pat / tb.extw[e]) % tb.radix[e])];
             int n = 0;
             for (int b = 0; b < 4; b++)
                 if ((m >> b) & 1u) s_bases[e][n++] = (uint8_t)b;
             s_n[e] = (uint32_t)n;
         }
-        for (int i = threadIdx.x; i < KP_MAXPOS * 8; i += blockDim.x) (&marg[0][0][0])[i] = 0;
-        if (threadIdx.x < 4) tot[threadIdx.x] = 0;
+        for (int i = threadIdx.x; i < KP_GREEDY_ACC; i += blockDim.x) marg[i] = 0;
         __syncthreads();
-        unsigned long long total = 1;
-        for (int e = 0; e < npos; e++) total *= s_n[e];
         unsigned long long aM = 0, aU = 0, aTM = 0, aTU = 0;
-        for (unsigned long long t = threadIdx.x; t < total; t += blockDim.x) {
+        const unsigned long long first = shared_node ? (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x : threadIdx.x;
+        const unsigned long long step = shared_node ? (unsigned long long)gridDim.x * blockDim.x : blockDim.x;
+        for (unsigned long long t = first; t < total; t += step) {
             unsigned long long r = t, kidx = 0;
             uint8_t pick[KP_MAXPOS];
             for (int e = 0; e < npos; e++) {
@@ -1031,79 +1032,114 @@ __global__ void __launch_bounds__(256) kp_greedy_level_kernel(const KpTables *ta
             if (testM) { aTM += (unsigned long long)testM[kidx]; aTU += (unsigned long long)testU[kidx]; }
             for (int e = 0; e < npos; e++)
                 if (s_n[e] > 1) {
-                    if (M) atomicAdd(&marg[e][pick[e]][0], M);
-                    if (U) atomicAdd(&marg[e][pick[e]][1], U);
+                    if (M) atomicAdd(&marg[(e * 4 + pick[e]) * 2 + 0], M);
+                    if (U) atomicAdd(&marg[(e * 4 + pick[e]) * 2 + 1], U);
                 }
         }
-        if (aM) atomicAdd(&tot[0], aM);
-        if (aU) atomicAdd(&tot[1], aU);
-        if (aTM) atomicAdd(&tot[2], aTM);
-        if (aTU) atomicAdd(&tot[3], aTU);
+        if (aM) atomicAdd(&marg[KP_MAXPOS * 8 + 0], aM);
+        if (aU) atomicAdd(&marg[KP_MAXPOS * 8 + 1], aU);
+        if (aTM) atomicAdd(&marg[KP_MAXPOS * 8 + 2], aTM);
+        if (aTU) atomicAdd(&marg[KP_MAXPOS * 8 + 3], aTU);
         __syncthreads();
-        if (threadIdx.x < 32) {
-            const int lane = threadIdx.x;
-            double lp0, l10;
-            const double self = kp_self_score_t<unsigned long long>(tot[0], tot[1], alpha, beta, penalty, logtab, K, lp0, l10);
-            // candidates in scan order: (position e, split j) -> rank pos_id[e] * 8 + j
-            double bv = self;
-            int brank = 0x7fffffff;
-            unsigned long long b1 = 0, b2 = 0;
-            int c = 0;
-            for (int e = 0; e < npos; e++) {
-                const unsigned m = s_mask[e];
-                const int ns = tb.ms_n[m];
-                for (int j = 0; j < ns; j++, c++) {
-                    if ((c & 31) != lane) continue;
-                    const unsigned m1 = tb.ms_c1[m][j], m2 = tb.ms_c2[m][j];
-                    unsigned long long M1 = 0, U1 = 0, M2 = 0, U2 = 0;
-                    for (int b = 0; b < 4; b++) {
-                        if ((m1 >> b) & 1u) { M1 += marg[e][b][0]; U1 += marg[e][b][1]; }
-                        if ((m2 >> b) & 1u) { M2 += marg[e][b][0]; U2 += marg[e][b][1]; }
-                    }
-                    double lpa, l1a;
-                    const double s1 = kp_self_score_t<unsigned long long>(M1, U1, alpha, beta, penalty, logtab, K, lpa, l1a);
-                    const double s2 = kp_self_score_t<unsigned long long>(M2, U2, alpha, beta, penalty, logtab, K, lpa, l1a);
-                    const double sum = KP_ADD(s1, s2);
-                    const int rank = tb.pos_id[e] * 8 + j;
-                    if (sum < bv || (sum == bv && rank < brank && brank != 0x7fffffff)) {
-                        const int d = (int)tb.mask_digit[e][m];
-                        bv = sum;
-                        brank = rank;
-                        b1 = nd.pat - (unsigned long long)(d - (int)tb.mask_digit[e][m1]) * tb.extw[e];
-                        b2 = nd.pat - (unsigned long long)(d - (int)tb.mask_digit[e][m2]) * tb.extw[e];
-                    }
+        for (int i = threadIdx.x; i < KP_GREEDY_ACC; i += blockDim.x)
+            if (marg[i]) atomicAdd(&acc[ni * KP_GREEDY_ACC + i], marg[i]);
+    }
+}
+
+// Step 2 of a depth: one warp per node scores the node and every candidate split from the marginals, decides, and
+// clears the node's accumulators for the next depth.
+__global__ void __launch_bounds__(256) kp_greedy_decide_kernel(const KpTables *tab, int has_test, double alpha, double beta,
+                                                               double penalty, int depth, const KpBtNode *cur,
+                                                               const unsigned long long *cur_size, KpBtNode *nxt,
+                                                               unsigned long long *nxt_size, KpGreedyLeaf *leaves,
+                                                               unsigned long long cap, unsigned long long *ctr,
+                                                               unsigned long long *acc)
+{
+    const KpTables &tb = *tab;
+    __shared__ double2 logtab[128];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) logtab[i] = make_double2(kpc_logTab[2 * i], kpc_logTab[2 * i + 1]);
+    __syncthreads();
+    const KpLogK K = kp_logk_load();
+    const unsigned long long ncur = ctr[2 + depth];
+    const int npos = tb.npos, lane = threadIdx.x & 31;
+    const unsigned long long nw = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    for (unsigned long long ni = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ni < ncur; ni += nw) {
+        const KpBtNode nd = cur[ni];
+        unsigned long long *marg = acc + ni * KP_GREEDY_ACC;
+        const unsigned long long tM = marg[KP_MAXPOS * 8 + 0], tU = marg[KP_MAXPOS * 8 + 1];
+        const unsigned long long hM = marg[KP_MAXPOS * 8 + 2], hU = marg[KP_MAXPOS * 8 + 3];
+        double lp0, l10;
+        const double self = kp_self_score_t<unsigned long long>(tM, tU, alpha, beta, penalty, logtab, K, lp0, l10);
+        // candidates in scan order: (position e, split j) -> rank pos_id[e] * 8 + j
+        double bv = self;
+        int brank = 0x7fffffff;
+        unsigned long long b1 = 0, b2 = 0, z1 = 0, z2 = 0;   // children and their sizes
+        const unsigned long long mysize = cur_size[ni];
+        int c = 0;
+        for (int e = 0; e < npos; e++) {
+            const int d = (int)((nd.pat / tb.extw[e]) % tb.radix[e]);
+            const unsigned m = tb.digit_mask[e][d];
+            const int ns = tb.ms_n[m];
+            for (int j = 0; j < ns; j++, c++) {
+                if ((c & 31) != lane) continue;
+                const unsigned m1 = tb.ms_c1[m][j], m2 = tb.ms_c2[m][j];
+                unsigned long long M1 = 0, U1 = 0, M2 = 0, U2 = 0;
+                for (int b = 0; b < 4; b++) {
+                    if ((m1 >> b) & 1u) { M1 += marg[(e * 4 + b) * 2]; U1 += marg[(e * 4 + b) * 2 + 1]; }
+                    if ((m2 >> b) & 1u) { M2 += marg[(e * 4 + b) * 2]; U2 += marg[(e * 4 + b) * 2 + 1]; }
+                }
+                double lpa, l1a;
+                const double s1 = kp_self_score_t<unsigned long long>(M1, U1, alpha, beta, penalty, logtab, K, lpa, l1a);
+                const double s2 = kp_self_score_t<unsigned long long>(M2, U2, alpha, beta, penalty, logtab, K, lpa, l1a);
+                const double sum = KP_ADD(s1, s2);
+                if (sum < bv) {   // within a lane the ranks only grow: a later equal sum never replaces an earlier one
+                    bv = sum;
+                    brank = tb.pos_id[e] * 8 + j;
+                    b1 = nd.pat - (unsigned long long)(d - (int)tb.mask_digit[e][m1]) * tb.extw[e];
+                    b2 = nd.pat - (unsigned long long)(d - (int)tb.mask_digit[e][m2]) * tb.extw[e];
+                    z1 = mysize / (unsigned)__popc(m) * (unsigned)__popc(m1);
+                    z2 = mysize / (unsigned)__popc(m) * (unsigned)__popc(m2);
                 }
             }
+        }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {   // strict minimum below the node's loss, earliest in scan order among equals
-                const double ov = __shfl_down_sync(0xffffffffu, bv, o);
-                const int orank = __shfl_down_sync(0xffffffffu, brank, o);
-                const unsigned long long o1 = __shfl_down_sync(0xffffffffu, b1, o), o2 = __shfl_down_sync(0xffffffffu, b2, o);
-                if (orank != 0x7fffffff && (ov < bv || (ov == bv && orank < brank))) { bv = ov; brank = orank; b1 = o1; b2 = o2; }
+        for (int o = 16; o > 0; o >>= 1) {   // strict minimum below the node's loss, earliest in scan order among equals
+            const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+            const int orank = __shfl_down_sync(0xffffffffu, brank, o);
+            const unsigned long long o1 = __shfl_down_sync(0xffffffffu, b1, o), o2 = __shfl_down_sync(0xffffffffu, b2, o);
+            const unsigned long long y1 = __shfl_down_sync(0xffffffffu, z1, o), y2 = __shfl_down_sync(0xffffffffu, z2, o);
+            if (orank != 0x7fffffff && (ov < bv || (ov == bv && orank < brank))) {
+                bv = ov; brank = orank; b1 = o1; b2 = o2; z1 = y1; z2 = y2;
             }
-            if (lane == 0) {
-                if (brank == 0x7fffffff) {   // no split beats the node: a leaf of the partition
-                    const unsigned long long li = atomicAdd(&ctr[0], 1ULL);
-                    if (li < cap) {
-                        KpGreedyLeaf L;
-                        L.pat = nd.pat; L.key = nd.key; L.loss = self;
-                        L.test = testM ? kp_test_ll_t<unsigned long long>(tot[2], tot[3], lp0, l10) : 0.0;
-                        leaves[li] = L;
-                    } else ctr[1] = 1;
-                } else if (depth >= 63) {
-                    ctr[1] = 1;
-                } else {
-                    const unsigned long long q = atomicAdd(&ctr[2 + depth + 1], 2ULL);
-                    if (q + 2 > cap) ctr[1] = 1;
-                    else {
-                        nxt[q].pat = b1; nxt[q].key = nd.key;
-                        nxt[q + 1].pat = b2; nxt[q + 1].key = nd.key | (1ULL << (63 - depth));
-                    }
+        }
+        __syncwarp();
+        for (int i = lane; i < KP_GREEDY_ACC; i += 32) marg[i] = 0;   // clean for the next depth
+        if (lane == 0) {
+            if (brank == 0x7fffffff) {   // no split beats the node: a leaf of the partition
+                const unsigned long long li = atomicAdd(&ctr[0], 1ULL);
+                if (li < cap) {
+                    KpGreedyLeaf L;
+                    L.pat = nd.pat; L.key = nd.key; L.loss = self;
+                    L.test = has_test ? kp_test_ll_t<unsigned long long>(hM, hU, lp0, l10) : 0.0;
+                    leaves[li] = L;
+                } else ctr[1] = 1;
+            } else if (depth >= 63) {
+                ctr[1] = 1;
+            } else {
+                const unsigned long long q = atomicAdd(&ctr[2 + depth + 1], 2ULL);
+                if (q + 2 > cap) ctr[1] = 1;
+                else {
+                    nxt[q].pat = b1; nxt[q].key = nd.key;
+                    nxt[q + 1].pat = b2; nxt[q + 1].key = nd.key | (1ULL << (63 - depth));
+                    nxt_size[q] = z1;
+                    nxt_size[q + 1] = z2;
                 }
             }
         }
     }
 }
+
+__global__ void kp_greedy_init_kernel(unsigned long long *size0, unsigned long long nkmer) { size0[0] = nkmer; }
 
 // rank sort of the greedy leaves by path key (depth-first, first child first): out[rank] = leaf
 __global__ void kp_greedy_sort_kernel(const KpGreedyLeaf *leaves, const unsigned long long *counts, unsigned long long cap,
