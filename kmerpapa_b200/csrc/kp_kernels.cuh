@@ -135,13 +135,16 @@ __device__ __forceinline__ float kp_min3(float a, float b, float c)
 }
 
 // Float32 lower bound of the self-score (w_numba.py:56-61) for the score filter, two patterns at a time with
-// the packed f32x2 instructions of sm_100 (FADD2/FMUL2/FFMA2).  The estimate's relative error is < 1e-5 (fast
-// log: < 2^-21 absolute; log(1-p) by its series below p = 2^-5; no cancellation: both terms are >= 0); the bound
-// subtracts a margin of 2e-4 |s| + 0.01.  A NaN (p == 0, ...) never skips the exact score.
+// the packed f32x2 instructions of sm_100 (FADD2/FMUL2/FFMA2).  Error budget of the estimate: counts -> float32 and
+// the arithmetic, relative < 1e-5 of |s| (no cancellation: both terms are >= 0; log(1-p) by its series below
+// p = 2^-5); __logf, ABSOLUTE 2^-21.4 for arguments in [0.5, 2] (rates near 1, or 1-p near 1 above the series range),
+// i.e. up to 2 * 3.6e-7 * (M + U) in s.  The bound subtracts 2e-4 |s| + 1e-6 (M + U) + 0.01.
+// A NaN (p == 0, ...) never skips the exact score.
 __device__ __forceinline__ float2 kp_score_lower_bound2(float2 Mf, float2 Uf, float alpha, float ab, float penalty)
 {
     const float2 num = __fadd2_rn(Mf, make_float2(alpha, alpha));
-    const float2 den = __fadd2_rn(__fadd2_rn(Mf, Uf), make_float2(ab, ab));
+    const float2 cnt = __fadd2_rn(Mf, Uf);
+    const float2 den = __fadd2_rn(cnt, make_float2(ab, ab));
     const float2 p = make_float2(__fdividef(num.x, den.x), __fdividef(num.y, den.y));
     const float2 lp = make_float2(__logf(p.x), __logf(p.y));
     // log(1-p) = -p (1 + p (1/2 + p (1/3 + p/4)))  for p < 2^-5
@@ -153,8 +156,9 @@ __device__ __forceinline__ float2 kp_score_lower_bound2(float2 Mf, float2 Uf, fl
     if (!(p.y < 0.03125f)) l1.y = __logf(1.0f - p.y);
     const float2 ll = __ffma2_rn(Mf, lp, __fmul2_rn(Uf, l1));                       // M log p + U log(1-p)  (<= 0)
     const float2 est = __ffma2_rn(ll, make_float2(-2.0f, -2.0f), make_float2(penalty, penalty));
-    // est - (2e-4 |est| + 0.01)
-    const float2 mar = __ffma2_rn(make_float2(fabsf(est.x), fabsf(est.y)), make_float2(2e-4f, 2e-4f), make_float2(0.01f, 0.01f));
+    // est - (2e-4 |est| + 1e-6 (M + U) + 0.01)
+    const float2 mar = __ffma2_rn(make_float2(fabsf(est.x), fabsf(est.y)), make_float2(2e-4f, 2e-4f),
+                                  __ffma2_rn(cnt, make_float2(1e-6f, 1e-6f), make_float2(0.01f, 0.01f)));
     return __fadd2_rn(est, make_float2(-mar.x, -mar.y));
 }
 

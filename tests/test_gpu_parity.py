@@ -176,6 +176,46 @@ def test_random_against_oracle(eng, oracle, gen_pat, seed):
     assert np.array_equal(patnums, oracle.backtrack(gen_pat, ref["split"]))
 
 
+@pytest.mark.parametrize("regime", ["rate_near_one", "half", "tiny_counts", "huge_counts", "zeros", "penalty_ties"])
+@pytest.mark.parametrize("gen_pat", ["NNNNN", "NNMNNN"])
+def test_count_regimes_against_oracle(eng, oracle, gen_pat, regime):
+    """Regimes that stress the score filter (a float32 bound decides whether the exact FP64 score is computed): rates
+    near 1 (absolute error of the fast log), rates around 1/2, counts of a few units, counts near 2^31, mostly empty
+    tables, and penalties that make many self-scores tie with split sums.  Full table + split codes vs the oracle."""
+    import zlib
+
+    rng = np.random.default_rng(zlib.crc32((gen_pat + regime).encode()))
+    _, nk, _ = oracle.plan_info(gen_pat)
+    if regime == "rate_near_one":
+        M = rng.integers(10 ** 5, 10 ** 6, size=nk)
+        U = rng.integers(0, 30, size=nk) * (rng.random(nk) < 0.5)
+    elif regime == "half":
+        U = rng.integers(10 ** 4, 10 ** 5, size=nk)
+        M = rng.binomial(2 * U, 0.5)
+    elif regime == "tiny_counts":
+        U = rng.integers(0, 4, size=nk)
+        M = rng.integers(0, 3, size=nk)
+    elif regime == "huge_counts":
+        U = rng.integers(10 ** 6, (2 ** 31 - 10 ** 6) // nk, size=nk)
+        M = rng.binomial(U, 0.001)
+    elif regime == "zeros":
+        keep = rng.random(nk) < 0.02
+        U = rng.integers(1, 5000, size=nk) * keep
+        M = rng.binomial(U, 0.05)
+    else:
+        U = np.full(nk, 1000)
+        M = np.full(nk, 10)
+    U[0], M[0] = max(U[0], 5), max(M[0], 1)
+    for alpha, pen in ((1.0, 4.0), (0.5, 0.0)) if regime != "penalty_ties" else ((1.0, 0.0), (1.0, 2.0)):
+        mu = M.sum() / (M.sum() + U.sum())
+        beta = alpha * (1 - mu) / mu
+        _, best, split, patnums = _run_single(eng, gen_pat, M, U, alpha, beta, pen)
+        ref = oracle.single_dp(gen_pat, M, U, alpha, beta, pen)
+        assert np.array_equal(_bits(best), _bits(ref["score"]))
+        assert np.array_equal(split, ref["split"])
+        assert np.array_equal(patnums, oracle.backtrack(gen_pat, ref["split"]))
+
+
 @pytest.mark.parametrize("gen_pat,seed", [("NNNNN", 21), ("RYNNANNKM", 22), ("VNNNH", 23), ("MMMMMMMMMM", 24),
                                           ("RYNNNANRY", 25), ("BBDHVVB", 26), ("N", 27), ("ACGT", 28), ("NNNSNN", 29)])
 def test_random_cv_job_against_oracle(eng, oracle, gen_pat, seed):
