@@ -51,3 +51,22 @@ def test_cli_cv_only_and_alias(tmp_path):
     assert rc == 0
     g = json.load(open(os.path.join(GOLDEN, "cli_cfg1_5mers.json")))
     assert open(cv).read() == g["cvfile"]
+
+
+def test_cli_sharded_over_gpus():
+    """The CLI under torchrun (CV jobs sharded over the ranks, NCCL gather) against the recorded reference runs."""
+    import subprocess
+    import sys
+
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29612", os.path.join(here, "mgpu_cli_check.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "CLI SHARDED OK" in r.stdout
+
