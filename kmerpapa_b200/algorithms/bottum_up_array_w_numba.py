@@ -28,16 +28,68 @@ def count_dtype(nmut, nunmut):
     return np.uint64 if nmut + nunmut > np.iinfo(np.uint32).max else np.uint32
 
 
+def _world():
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl":
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
+def _sharded_partition(plan, eM, eU, max_count, alpha, beta, penalty, rank, world):
+    """One DP over all ranks of the process group (kmerpapa_b200/sharded.py).  Returns None when this general pattern
+    cannot be sharded over `world` ranks (every rank takes the same decision: it depends on the plan only)."""
+    import torch
+
+    from .. import sharded
+    from .._native import KpError
+
+    import torch.distributed as dist
+
+    table_bytes = int(plan.info.table_elems) * 4 + int(plan.info.kept_elems) * 2
+    total = torch.cuda.get_device_properties(plan.device).total_memory
+    if table_bytes < 0.8 * total:
+        # the table fits one GPU: mapping the peers' shards (CUDA IPC, 0.1-0.3 s) costs more than the one DP gains
+        # (tools/shard_overhead.py); callers that run many DPs keep a ShardedDP(replicate=True) themselves
+        return None
+    try:
+        sh = sharded.ShardedDP(plan, rank, world, replicate=False)
+    except KpError:
+        sh = None
+    ok = torch.tensor([0 if sh is None else 1], dtype=torch.int32, device=plan.device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks shard, or none does
+    if int(ok.item()) == 0:
+        if sh is not None:
+            sh.close()
+        return None
+    try:
+        sh.connect()
+        sh.run(eM, eU, max_count, alpha, beta, penalty)
+        return sh.top_score(), sh.backtrack()
+    finally:
+        sh.close()
+
+
 def partition_from_arrays(gen_pat, codes, pos, neg, alpha, beta, penalty, device=None, want_counts=False):
     """Array-level entry (host buffers in, host results out): returns (np.float32 loss,
-    dense pattern numbers of the partition in emission order[, (M, U) per pattern])."""
+    dense pattern numbers of the partition in emission order[, (M, U) per pattern]).
+    Inside an NCCL process group (torchrun, one process per GPU) a DP whose table does not fit one GPU is sharded over
+    the ranks (capacity mode of kmerpapa_b200/sharded.py); every rank gets the result."""
     plan = get_plan(gen_pat, device)
     kM, kU = plan.pack_counts(codes, pos, neg)
     eM, eU = plan.expand(kM, kU)
     max_count = int(pos.sum()) + int(neg.sum())
-    best, kept = plan.dp_single(eM, eU, max_count, alpha, beta, penalty)
-    patnums = plan.backtrack(best, kept)
-    loss = plan.top_score(best)
+    rank, world = _world()
+    res = _sharded_partition(plan, eM, eU, max_count, alpha, beta, penalty, rank, world) if world > 1 else None
+    if res is not None:
+        loss, patnums = res
+    else:
+        best, kept = plan.dp_single(eM, eU, max_count, alpha, beta, penalty)
+        patnums = plan.backtrack(best, kept)
+        loss = plan.top_score(best)
     if want_counts:
         return loss, patnums, plan.pattern_counts(kM, kU, patnums)
     return loss, patnums
