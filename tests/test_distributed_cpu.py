@@ -1,6 +1,7 @@
 """Job sharding + gather over torch.distributed with the gloo backend, world_size 2, on CPU.
 The per-job runner is a stand-in (the CPU oracle on a small general pattern): what is under test is the
-host logic every rank runs — same fold tables, contiguous job chunks, one all_gather, identical selection."""
+host logic every rank runs — the fold sampler one fold ahead of the jobs (the runner has the GPU runner's
+streaming interface), contiguous job chunks, one all_gather, identical selection."""
 import os
 import sys
 
@@ -32,6 +33,14 @@ class OracleRunner:
 
     def set_folds(self, Mf, Uf):
         self.Mf, self.Uf = Mf, Uf
+
+    # the GPU runner's streaming interface: folds arrive one at a time from the sampler thread
+    def begin_folds(self, nkmer, nfolds):
+        self.Mf = np.zeros((nkmer, nfolds), dtype=np.uint64)
+        self.Uf = np.zeros((nkmer, nfolds), dtype=np.uint64)
+
+    def set_fold(self, f, M, U):
+        self.Mf[:, f], self.Uf[:, f] = M, U
 
     def run(self, f, alpha, beta, penalty):
         self.calls += 1
