@@ -276,7 +276,7 @@ def bench_single(args, rank, world, local):
                    "loss": float(loss), "l2": "score table 11 GB >> 126 MB L2, no flush needed",
                    "replicas": world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": load_traffic("single_dp_bytes"), "kernel": "kp_dp_rows_kernel (fused lazy score + min-plus), one launch for all 16 waves of a DP",
+                     "traffic": load_traffic("single_dp_bytes"), "kernel": "kp_dp_rows_kernel (fused lazy score + min-plus), all 16 wave launches of one DP",
                      "kernel_ms": dp_ms, "algorithmic_bytes_per_pattern": ALGO_BYTES_SINGLE, "peak_kind": peak_kind,
                      "design_bytes_per_pattern": 4.0 * 3616 / 3375 * (1 + 16.7) + 2 * 226 / 3375.0},
         "e2e": {"value": world * npat / (e2e_ms / 1e3), "unit": "patterns/s", "ms_per_step": e2e_ms,

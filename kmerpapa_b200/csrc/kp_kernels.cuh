@@ -216,9 +216,11 @@ struct KpDpParams {
 //     rank in their top 4 bits).
 //   2 (replicated, speed): every rank holds a full-size table; a finished row is stored locally AND into the
 //     table of every peer that owns a superset digit (posted NVLink writes), so all reads stay local.
-//   3 (one GPU, single launch): tile_list holds every wave back to back and tiles are claimed in that order by the
-//     resident warps (one CTA per SM, all resident); a tile spins until its child tiles are flagged done.  Claiming
-//     in order makes this deadlock-free: every child was claimed earlier, by a warp that is running.
+//   3 (one GPU, single launch; opt-in): tile_list holds every wave back to back and tiles are claimed in that order by
+//     the resident warps (one CTA per SM, all resident); a tile spins until its child tiles are flagged done.  Claiming
+//     in order makes this deadlock-free: every child was claimed earlier, by a warp that is running.  The table is then
+//     written and read by the same kernel, so its loads are ld.global.cg instead of the read-only (.nc) path - which
+//     costs more than the overlapped wave tails gain in a sustained run.
 template <int R0, bool WIDE, int RP, int SHARD>
 __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const KpDpParams p)
 {
@@ -529,7 +531,9 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
                     if (leafrow) need |= (1u << NB) - 1u;
                 }
                 // ---- exact float64 self-score of the patterns that passed the filter ----
-                float sfx[NG * 4];   // indexed at run time below: lives in local memory, rarely touched
+                float sfx[NG * 4];   // one register per digit: written below by compile-time index under a predicate
+#pragma unroll
+                for (int c = 0; c < NG * 4; c++) sfx[c] = 0.f;
                 uint32_t rupm = 0;
                 if (need) {
                     const KpLogK K = kp_logk_load();
@@ -547,7 +551,9 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
                         else s_ = kp_self_score_t<C>(M_, U_, alpha, beta, penalty, logtab, K, lp_, l1_);
                         const float sf = __double2float_rn(s_);
                         if ((double)sf > s_) rupm |= 1u << d;
-                        sfx[d] = sf;
+#pragma unroll
+                        for (int c = 0; c < R0; c++)
+                            if (c == d) sfx[c] = sf;
                     }
                 }
                 // ---- register position: in-register splits + self-score compare, digit by digit.
@@ -691,28 +697,60 @@ __global__ void kp_expand_base_kernel(const KpTables *tab, unsigned long long nk
 __global__ void kp_expand_pass_kernel(const KpTables *tab, int hi, unsigned long long total, long long *expM, long long *expU)
 {
     const KpTables &tb = *tab;
-    const uint32_t tk = tb.tile_kmers;
+    // per-pass constants of the mixed-radix decode, once per CTA (the table struct lives in global memory)
+    __shared__ uint32_t s_n[KP_MAXPOS], s_w[KP_MAXPOS], s_add[KP_MAXPOS];
+    __shared__ uint32_t s_src[16][4];   // digit of the pass position -> tile offsets of its single-nucleotide sources
+    __shared__ uint32_t s_nsrc[16];
+    const int nhigh = tb.nhigh;
     const int e = tb.highpos[hi];
-    const uint32_t hw = tb.highw[e];
+    const uint32_t tk = tb.tile_kmers;
+    if (threadIdx.x < nhigh) {
+        const int h = threadIdx.x, f = tb.highpos[h];
+        const uint32_t nb = tb.nbase[f];
+        s_n[h] = h < hi ? tb.radix[f] : (h == hi ? tb.radix[f] - nb : nb);
+        s_add[h] = h == hi ? nb : 0;   // the pass position enumerates its multi-letter digits only
+        s_w[h] = tb.highw[f];
+    }
+    if (threadIdx.x < 16) {
+        const int d = threadIdx.x;
+        int n = 0;
+        if (d < tb.radix[e]) {
+            const uint32_t m = tb.digit_mask[e][d];
+            for (int b = 0; b < 4; b++)
+                if ((m >> b) & 1u) s_src[d][n++] = (uint32_t)(d - tb.mask_digit[e][1u << b]) * tb.highw[e];
+        }
+        s_nsrc[d] = (uint32_t)n;
+    }
+    __syncthreads();
     for (unsigned long long x = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; x < total;
          x += (unsigned long long)gridDim.x * blockDim.x) {
-        const uint32_t kl = (uint32_t)(x % tk);
-        unsigned long long r = x / tk;
-        uint32_t tile = 0, d = 0;
-        for (int h = 0; h < tb.nhigh; h++) {
-            const int f = tb.highpos[h];
-            const uint32_t nb = tb.nbase[f];
-            const uint32_t n = h < hi ? tb.radix[f] : (h == hi ? tb.radix[f] - nb : nb);
-            uint32_t dig = (uint32_t)(r % n);   // a single-nucleotide digit is its base index
-            r /= n;
-            if (h == hi) { dig += nb; d = dig; }
-            tile += dig * tb.highw[f];
+        uint32_t kl, tile = 0, d = 0;
+        if (total <= 0xFFFFFFFFull) {   // 32-bit index arithmetic (every realistic size)
+            const uint32_t x32 = (uint32_t)x;
+            kl = x32 % tk;
+            uint32_t r = x32 / tk;
+            for (int h = 0; h < nhigh; h++) {
+                const uint32_t n = s_n[h];
+                const uint32_t dig = r % n + s_add[h];   // a single-nucleotide digit is its base index
+                r /= n;
+                if (h == hi) d = dig;
+                tile += dig * s_w[h];
+            }
+        } else {
+            kl = (uint32_t)(x % tk);
+            unsigned long long r = x / tk;
+            for (int h = 0; h < nhigh; h++) {
+                const uint32_t n = s_n[h];
+                const uint32_t dig = (uint32_t)(r % n) + s_add[h];
+                r /= n;
+                if (h == hi) d = dig;
+                tile += dig * s_w[h];
+            }
         }
-        const uint32_t m = tb.digit_mask[e][d];
         long long am = 0, au = 0;
-        for (int b = 0; b < 4; b++) {
-            if (!((m >> b) & 1u)) continue;
-            const size_t src = (size_t)(tile - (d - tb.mask_digit[e][1u << b]) * hw) * tk + kl;
+        const uint32_t ns = s_nsrc[d];
+        for (uint32_t i = 0; i < ns; i++) {
+            const size_t src = (size_t)(tile - s_src[d][i]) * tk + kl;
             am += expM[src];
             au += expU[src];
         }

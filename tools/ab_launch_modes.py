@@ -10,10 +10,10 @@ kM, kU = plan.pack_counts(synthetic.codes_of(kmers), pos, neg)
 eM, eU = plan.expand(kM, kU)
 mc = int(pos.sum() + neg.sum()); mu = int(pos.sum()) / mc; beta = (1 - mu) / mu
 res = {0: [], 1: []}
-for rep in range(24):
+for rep in range(int(os.environ.get("AB_REPS", "24"))):
     mode = rep & 1
-    if mode: os.environ["KP_WAVE_LAUNCHES"] = "1"
-    else: os.environ.pop("KP_WAVE_LAUNCHES", None)
+    if mode: os.environ.pop("KP_ONE_LAUNCH", None)
+    else: os.environ["KP_ONE_LAUNCH"] = "1"
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); plan.dp_single(eM, eU, mc, 1.0, beta, 6.0); e1.record(); torch.cuda.synchronize()

@@ -5,6 +5,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("KP_ONE_LAUNCH", "1")   # the mode under test (opt-in)
 import torch
 
 from kmerpapa_b200 import synthetic
