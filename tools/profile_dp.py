@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One 9-mer single DP (and optionally one CV job) for ncu: `python tools/profile_dp.py [single|cv] [gen_pat]`.
-One warm-up DP, then one profiled DP; kernels of interest are named kp_dp_wave_kernel."""
+`reps` DPs (the first one warms up); the kernel of interest is kp_dp_rows_kernel (16 launches per DP, one per wave)."""
 import os
 import sys
 
