@@ -331,7 +331,8 @@ static int launch_dp(kp_plan *p, bool wide, KpDpParams prm, cudaStream_t st)
     KP_CUDA(cudaMemsetAsync(p->d_counters, 0, sizeof(uint32_t) * 128, st));
     // Opt-in (KP_ONE_LAUNCH=1) for large all-N problems: ONE launch over every wave; tiles wait for their child tiles, not
     // for a kernel boundary.  Not the default: see DESIGN.md section 4.
-    if (p->d_tile_done && t.ntiles >= (uint64_t)8 * p->sm_count * nw && getenv("KP_ONE_LAUNCH")) {
+    const char *one = getenv("KP_ONE_LAUNCH");
+    if (p->d_tile_done && t.ntiles >= (uint64_t)8 * p->sm_count * nw && one && one[0] == '1') {
         KP_CUDA(cudaMemsetAsync(p->d_tile_done, 0, t.ntiles, st));
         KP_CUDA(cudaMemsetAsync(p->d_err, 0, sizeof(int), st));
         prm.tile_list = p->d_tiles;

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Soak test of the single-launch DP (tiles wait on completion flags of other tiles): the same DP many times, the whole
-score table and the kept flags must come out bit-identical every time.  python tools/soak_dp.py [reps] [gen_pat]"""
+"""Soak test of the DP: the same DP many times, the whole score table and the kept flags must come out bit-identical
+every time.  Default: the opt-in single-launch mode (tiles wait on completion flags of other tiles); KP_ONE_LAUNCH=0
+in the environment soaks the default one-launch-per-wave mode.  python tools/soak_dp.py [reps] [gen_pat]"""
 import os
 import sys
 
