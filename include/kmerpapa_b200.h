@@ -121,9 +121,9 @@ int kp_gather_kept(kp_plan *plan, const uint16_t *d_kept, uint64_t first, uint64
 
 /*
  * One cross-validation job = one fold x alpha x penalty.  d_exp?tot: all-fold totals, d_exp?test: the fold's
- * held-out counts (both from kp_expand_counts).  Train counts are formed on the device as total - held-out into
- * the workspace tables d_exp?tr (int64[expanded_elems]); the DP of kp_dp_single then runs on them and fills
- * d_train (float32[table_elems]) and d_kept.  The reference additionally carries the held-out loss of every
+ * held-out counts (both from kp_expand_counts).  Train counts are total - held-out; the subtraction commutes with
+ * the sums of the expansion, so the DP kernel of kp_dp_single forms them on the fly when it reads a tile's base counts
+ * (no train table exists) and fills d_train (float32[table_elems]) and d_kept.  The reference additionally carries the held-out loss of every
  * pattern's best partition but only reads it at the general pattern: that number is the float32 sum, in tree
  * order, of the held-out losses of the leaves of the optimal partition, and is computed here from the
  * backtracked tree (d_ws/cap as for kp_backtrack).
@@ -131,15 +131,14 @@ int kp_gather_kept(kp_plan *plan, const uint16_t *d_kept, uint64_t first, uint64
  */
 int kp_dp_cv_job(kp_plan *plan, const int64_t *d_expMtot, const int64_t *d_expUtot, const int64_t *d_expMtest,
                  const int64_t *d_expUtest, uint64_t max_count, double alpha, double beta_fold, double penalty,
-                 int64_t *d_expMtr, int64_t *d_expUtr, float *d_train, uint16_t *d_kept, void *d_ws, uint64_t cap,
-                 float *h_top, void *stream);
+                 float *d_train, uint16_t *d_kept, void *d_ws, uint64_t cap, float *h_top, void *stream);
 
 /*
  * Held-out loss of the best partition of pattern `root` after kp_dp_cv_job (the reference's test_score_mem[root],
- * bottum_up_array_penalty_plus_pseudo_CV.py:46-51, :71-78).  Synchronises.
+ * bottum_up_array_penalty_plus_pseudo_CV.py:46-51, :71-78), same total / held-out tables as the job.  Synchronises.
  */
-int kp_cv_heldout(kp_plan *plan, const float *d_train, const uint16_t *d_kept, const int64_t *d_expMtr,
-                  const int64_t *d_expUtr, const int64_t *d_expMtest, const int64_t *d_expUtest, double alpha,
+int kp_cv_heldout(kp_plan *plan, const float *d_train, const uint16_t *d_kept, const int64_t *d_expMtot,
+                  const int64_t *d_expUtot, const int64_t *d_expMtest, const int64_t *d_expUtest, double alpha,
                   double beta_fold, double penalty, uint64_t root, void *d_ws, uint64_t cap, float *h_test, void *stream);
 
 /* Counts of arbitrary patterns (dense numbers) straight from the k-mer tables.  Synchronises. */

@@ -50,7 +50,7 @@ SYMBOLS = {
     "kp_split_codes": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp]),
     "kp_gather_table": (_int, [_vp, _vp, _u64, _u64, _vp, _vp]),
     "kp_gather_kept": (_int, [_vp, _vp, _u64, _u64, _vp, _vp]),
-    "kp_dp_cv_job": (_int, [_vp, _vp, _vp, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp]),
+    "kp_dp_cv_job": (_int, [_vp, _vp, _vp, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp, _vp, _vp, _u64, _vp, _vp]),
     "kp_cv_heldout": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _u64, _vp, _u64, _vp, _vp]),
     "kp_pattern_counts": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp]),
     "kp_pattern_offset": (_int, [_vp, _u64, ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(ctypes.c_uint32)]),

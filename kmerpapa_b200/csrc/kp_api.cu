@@ -382,8 +382,18 @@ static int launch_dp(kp_plan *p, bool wide, KpDpParams prm, cudaStream_t st)
     return 0;
 }
 
+static int dp_counts(kp_plan *p, const int64_t *d_expM, const int64_t *d_expU, const int64_t *d_subM, const int64_t *d_subU,
+                     uint64_t max_count, double alpha, double beta, double penalty, float *d_best, uint16_t *d_kept, void *stream);
+
 int kp_dp_single(kp_plan *p, const int64_t *d_expM, const int64_t *d_expU, uint64_t max_count, double alpha, double beta,
                  double penalty, float *d_best, uint16_t *d_kept, void *stream)
+{
+    return dp_counts(p, d_expM, d_expU, nullptr, nullptr, max_count, alpha, beta, penalty, d_best, d_kept, stream);
+}
+
+// the DP on the counts d_expM - d_subM, d_expU - d_subU (d_sub*: null for none)
+static int dp_counts(kp_plan *p, const int64_t *d_expM, const int64_t *d_expU, const int64_t *d_subM, const int64_t *d_subU,
+                     uint64_t max_count, double alpha, double beta, double penalty, float *d_best, uint16_t *d_kept, void *stream)
 {
     if (!p) return fail("kp_dp_single: null plan");
     KP_CUDA(cudaSetDevice(p->device));
@@ -394,6 +404,8 @@ int kp_dp_single(kp_plan *p, const int64_t *d_expM, const int64_t *d_expU, uint6
     prm.rowtab = p->d_rowtab;
     prm.e0 = (const long long *)d_expM;
     prm.e1 = (const long long *)d_expU;
+    prm.s0 = (const long long *)d_subM;
+    prm.s1 = (const long long *)d_subU;
     prm.alpha = alpha; prm.beta = beta; prm.penalty = penalty;
     prm.best = d_best;
     prm.flags = d_kept;
@@ -453,7 +465,7 @@ int kp_backtrack(kp_plan *p, const float *d_best, const uint16_t *d_kept, void *
     return 0;
 }
 
-int kp_cv_heldout(kp_plan *p, const float *d_train, const uint16_t *d_kept, const int64_t *d_expMtr, const int64_t *d_expUtr,
+int kp_cv_heldout(kp_plan *p, const float *d_train, const uint16_t *d_kept, const int64_t *d_expMtot, const int64_t *d_expUtot,
                   const int64_t *d_expMtest, const int64_t *d_expUtest, double alpha, double beta_fold, double penalty,
                   uint64_t root, void *d_ws, uint64_t cap, float *h_test, void *stream)
 {
@@ -465,7 +477,7 @@ int kp_cv_heldout(kp_plan *p, const float *d_train, const uint16_t *d_kept, cons
     unsigned long long *sorted, *keys, *ctr;
     float *vals;
     if (backtrack_device(p, single_view(p, d_train, d_kept), d_ws, cap, root, st, &sorted, &keys, &vals, &ctr)) return 1;
-    kp_cv_leaf_kernel<<<p->sm_count, 128, 0, st>>>(p->d_tab, p->d_rowtab, (const long long *)d_expMtr, (const long long *)d_expUtr,
+    kp_cv_leaf_kernel<<<p->sm_count, 128, 0, st>>>(p->d_tab, p->d_rowtab, (const long long *)d_expMtot, (const long long *)d_expUtot,
                                                    (const long long *)d_expMtest, (const long long *)d_expUtest, alpha, beta_fold,
                                                    penalty, sorted, ctr, cap, vals);
     p->launches++;
@@ -485,23 +497,18 @@ int kp_cv_heldout(kp_plan *p, const float *d_train, const uint16_t *d_kept, cons
 
 int kp_dp_cv_job(kp_plan *p, const int64_t *d_expMtot, const int64_t *d_expUtot, const int64_t *d_expMtest,
                  const int64_t *d_expUtest, uint64_t max_count, double alpha, double beta_fold, double penalty,
-                 int64_t *d_expMtr, int64_t *d_expUtr, float *d_train, uint16_t *d_kept, void *d_ws, uint64_t cap,
-                 float *h_top, void *stream)
+                 float *d_train, uint16_t *d_kept, void *d_ws, uint64_t cap, float *h_top, void *stream)
 {
-    if (!p) return fail("kp_dp_cv_job: null plan");
+    if (!p || !d_expMtest || !d_expUtest) return fail("kp_dp_cv_job: null argument");
     cudaStream_t st = (cudaStream_t)stream;
     KP_CUDA(cudaSetDevice(p->device));
     const KpTables &t = p->host.t;
-    const uint64_t nexp = (uint64_t)t.ntiles * t.tile_kmers;
-    // train counts = total - held-out, on the expanded tables (sums commute with the subtraction)
-    kp_train_counts_kernel<<<grid_for(nexp, 256, p->sm_count), 256, 0, st>>>((const long long *)d_expMtot, (const long long *)d_expMtest,
-                                                                             (long long *)d_expMtr, nexp);
-    kp_train_counts_kernel<<<grid_for(nexp, 256, p->sm_count), 256, 0, st>>>((const long long *)d_expUtot, (const long long *)d_expUtest,
-                                                                             (long long *)d_expUtr, nexp);
-    p->launches += 2;
-    if (kp_dp_single(p, d_expMtr, d_expUtr, max_count, alpha, beta_fold, penalty, d_train, d_kept, stream)) return 1;
+    // train counts = total - held-out: the subtraction commutes with the sums of the expansion, so it is done by the DP
+    // kernel (and the leaf kernel) when they read the tile's base counts; no train table is materialised
+    if (dp_counts(p, d_expMtot, d_expUtot, d_expMtest, d_expUtest, max_count, alpha, beta_fold, penalty, d_train, d_kept, stream))
+        return 1;
     if (h_top) {
-        if (kp_cv_heldout(p, d_train, d_kept, d_expMtr, d_expUtr, d_expMtest, d_expUtest, alpha, beta_fold, penalty, UINT64_MAX,
+        if (kp_cv_heldout(p, d_train, d_kept, d_expMtot, d_expUtot, d_expMtest, d_expUtest, alpha, beta_fold, penalty, UINT64_MAX,
                           d_ws, cap, h_top + 1, stream))
             return 1;
         uint64_t tile; uint32_t srow, d0;

@@ -194,6 +194,7 @@ struct KpDpParams {
     int leaf_wave;              // wave 0: rows of level 0 hold k-mers at the single-nucleotide digits
     int pf_dist;                // L2 prefetch distance of the child-tile stream, in (32 rows x 1 split) steps
     const long long *e0, *e1;   // expanded counts M, U  [ntiles][tile_kmers]
+    const long long *s0, *s1;   // CV job: held-out expanded counts, subtracted on the fly (train = total - held-out); else null
     double alpha, beta, penalty;
     float *best;                // best loss per pattern (sharded: this rank's shard)
     uint16_t *flags;            // per row, bit d set = pattern kept whole
@@ -342,8 +343,8 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
         // ---- base counts of the tile ----
         for (uint32_t kl = lane; kl < tk; kl += 32) {
             size_t g = (size_t)tile * tk + kl;
-            bc[kl * 2 + 0] = (C)p.e0[g];
-            bc[kl * 2 + 1] = (C)p.e1[g];
+            bc[kl * 2 + 0] = (C)(p.s0 ? p.e0[g] - p.s0[g] : p.e0[g]);
+            bc[kl * 2 + 1] = (C)(p.s1 ? p.e1[g] - p.s1[g] : p.e1[g]);
         }
         __syncwarp();
         const int nhs = *s_nhs;
@@ -634,13 +635,6 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
 // the optimal partition is then summed along the partition tree (_CV.py:46-51, :71-78): a leaf contributes
 // the float32 held-out loss of the unsplit pattern, an inner node the float32 sum of its two children.
 // ---------------------------------------------------------------------------------------------------
-__global__ void kp_train_counts_kernel(const long long *tot, const long long *held, long long *train, unsigned long long n)
-{
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * blockDim.x)
-        train[i] = tot[i] - held[i];
-}
-
 // ---------------------------------------------------------------------------------------------------
 // K1: scatter packed k-mers into the dense k-mer tables (duplicates add, like read_dict)
 // ---------------------------------------------------------------------------------------------------
@@ -824,7 +818,7 @@ __device__ __forceinline__ void kp_counts_from_expanded(const KpTables &tb, cons
 }
 
 // held-out loss of every leaf of a backtracked partition: RN_f32 of _CV.py:73-78 (level >= 1) or :15-20 (k-mers)
-__global__ void kp_cv_leaf_kernel(const KpTables *tab, const uint8_t *rowtab, const long long *eMtr, const long long *eUtr,
+__global__ void kp_cv_leaf_kernel(const KpTables *tab, const uint8_t *rowtab, const long long *eMtot, const long long *eUtot,
                                   const long long *eMte, const long long *eUte, double alpha, double beta, double penalty,
                                   const unsigned long long *pats, const unsigned long long *counts, unsigned long long cap,
                                   float *out)
@@ -841,8 +835,10 @@ __global__ void kp_cv_leaf_kernel(const KpTables *tab, const uint8_t *rowtab, co
          i += (unsigned long long)gridDim.x * blockDim.x) {
         KpLoc L = kp_locate_dev(tb, srow_of_row, pats[i]);
         unsigned long long Mtr, Utr, Mte, Ute;
-        kp_counts_from_expanded(tb, rowtab, eMtr, eUtr, L.tile, L.srow, L.d0, Mtr, Utr);
+        kp_counts_from_expanded(tb, rowtab, eMtot, eUtot, L.tile, L.srow, L.d0, Mtr, Utr);
         kp_counts_from_expanded(tb, rowtab, eMte, eUte, L.tile, L.srow, L.d0, Mte, Ute);
+        Mtr -= Mte;   // train = total - held-out
+        Utr -= Ute;
         bool kmer = row_level[L.srow] == 0 && L.d0 < (uint32_t)tb.nb0;
         unsigned long long x = L.tile;
         for (int h = 0; h < tb.nhigh; h++) {

@@ -162,17 +162,14 @@ class PartitionPlan:
         DP runs and the device tables (train, kept) are returned."""
         torch = _torch()
         n = int(self.info.table_elems)
-        ne = int(self.info.expanded_elems)
         train = self._buffer("cvtrain", n, torch.float32)
         kept = self._buffer("cvkept", int(self.info.kept_elems), torch.int16)
-        eMtr = self._buffer("cv_expMtr", ne, torch.int64)
-        eUtr = self._buffer("cv_expUtr", ne, torch.int64)
         top = (ctypes.c_float * 2)()
         while True:
             ws = self._buffer("btws", int(self.lib.kp_backtrack_ws_bytes(cap)), torch.uint8)
             rc = self.lib.kp_dp_cv_job(self.handle, eMtot.data_ptr(), eUtot.data_ptr(), eMte.data_ptr(), eUte.data_ptr(),
-                                       int(max_count), float(alpha), float(beta), float(penalty), eMtr.data_ptr(),
-                                       eUtr.data_ptr(), train.data_ptr(), kept.data_ptr(), ws.data_ptr(), cap,
+                                       int(max_count), float(alpha), float(beta), float(penalty),
+                                       train.data_ptr(), kept.data_ptr(), ws.data_ptr(), cap,
                                        ctypes.cast(top, ctypes.c_void_p) if read_top else None, self._stream())
             if rc == 0:
                 break
@@ -181,7 +178,7 @@ class PartitionPlan:
                 cap *= 8
                 continue
             raise KpError("kp_dp_cv_job: " + msg)
-        self._cv_state = (eMtr, eUtr, eMte, eUte, float(alpha), float(beta), float(penalty))
+        self._cv_state = (eMtot, eUtot, eMte, eUte, float(alpha), float(beta), float(penalty))
         if not read_top:
             return train, kept
         return np.float32(top[0]), np.float32(top[1])
@@ -189,11 +186,11 @@ class PartitionPlan:
     def cv_heldout(self, root, cap=65536):
         """Held-out loss of the best partition of pattern `root` for the last cv_job (reference: test_score_mem[root])."""
         torch = _torch()
-        eMtr, eUtr, eMte, eUte, alpha, beta, penalty = self._cv_state
+        eMtot, eUtot, eMte, eUte, alpha, beta, penalty = self._cv_state
         ws = self._buffer("btws", int(self.lib.kp_backtrack_ws_bytes(cap)), torch.uint8)
         out = ctypes.c_float(0)
         check(self.lib.kp_cv_heldout(self.handle, self._buf["cvtrain"].data_ptr(), self._buf["cvkept"].data_ptr(),
-                                     eMtr.data_ptr(), eUtr.data_ptr(), eMte.data_ptr(), eUte.data_ptr(), alpha, beta, penalty,
+                                     eMtot.data_ptr(), eUtot.data_ptr(), eMte.data_ptr(), eUte.data_ptr(), alpha, beta, penalty,
                                      int(root), ws.data_ptr(), cap, ctypes.byref(out), self._stream()), "kp_cv_heldout")
         return np.float32(out.value)
 
