@@ -49,6 +49,7 @@ struct kp_plan {
     uint64_t launches = 0;
     int nwarps[2] = {0, 0};  // warps (= tiles in flight) per CTA of the DP kernel [wide]
     size_t smem_optin = 0;
+    bool coop_launch = false;        // the device supports cooperative launches (backtrack: all depths in one launch)
 };
 
 // the all-N tile shape (register radix 15, two N row positions: 225 rows) gets its row pitch at compile time
@@ -165,6 +166,7 @@ static int plan_create(const char *gen_pat, int device, bool lattice, kp_plan **
         KP_CUDA(cudaMalloc(&p->d_tile_done, tw.size()));
     }
     p->smem_optin = prop.sharedMemPerBlockOptin;
+    p->coop_launch = prop.cooperativeLaunch != 0 && !getenv("KP_NO_COOP_BACKTRACK");
     for (int wide = 0; wide < 2; wide++) {
         size_t fixed = 2048 + t.rt_bytes, per_warp = t.warp_smem_bytes[wide];
         int nw = fixed < p->smem_optin ? (int)((p->smem_optin - fixed) / per_warp) : 0;
@@ -428,7 +430,24 @@ static int backtrack_device(kp_plan *p, const KpView &vw, void *d_ws, uint64_t c
     const int levels = (int)p->host.t.total_level + 1;
     int grid = (int)((cap + 7) / 8);
     if (grid > p->sm_count * 2) grid = p->sm_count * 2;
-    for (int d = 0; d < levels && d < 64; d++) {
+    // all depths in one cooperative launch (grid-wide barrier between depths); one launch per depth if the device
+    // cannot run the grid co-resident
+    bool fused = false;
+    if (p->coop_launch) {
+        int nlev = levels < 64 ? levels : 64;
+        int cgrid = grid < p->sm_count ? grid : p->sm_count;
+        const KpTables *a_tab = p->d_tab;
+        const uint8_t *a_row = p->d_rowtab;
+        void *args[] = {(void *)&a_tab, (void *)&a_row, (void *)&vw, (void *)&nlev, (void *)&fa, (void *)&fb, (void *)&leaves,
+                        (void *)&cap, (void *)&ctr};
+        if (cudaLaunchCooperativeKernel((const void *)kp_backtrack_all_kernel, dim3(cgrid), dim3(256), args, 0, st) == cudaSuccess) {
+            fused = true;
+            p->launches++;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    for (int d = 0; !fused && d < levels && d < 64; d++) {
         kp_backtrack_level_kernel<<<grid, 256, 0, st>>>(p->d_tab, p->d_rowtab, vw, d, (d & 1) ? fb : fa,
                                                         (d & 1) ? fa : fb, leaves, cap, ctr);
         p->launches++;

@@ -892,18 +892,17 @@ struct KpBtNode { unsigned long long pat, key; };
 // One launch per depth of the partition tree, one warp per node: lane e evaluates the splits of effective
 // position e (their 2 x nsplit child reads are independent and overlap), then the warp takes the
 // lexicographic minimum of (child sum, scan rank).  ctr: [0] leaves, [1] overflow flag, [2 + d] nodes at depth d.
-__global__ void __launch_bounds__(256) kp_backtrack_level_kernel(const KpTables *tab, const uint8_t *rowtab, const KpView vw,
-                                                                 int depth, const KpBtNode *cur, KpBtNode *nxt,
-                                                                 KpBtNode *leaves, unsigned long long cap,
-                                                                 unsigned long long *ctr)
+__device__ __forceinline__ void kp_backtrack_level(const KpTables &tb, const uint8_t *rowtab, const KpView &vw, int depth,
+                                                   const KpBtNode *cur, KpBtNode *nxt, KpBtNode *leaves,
+                                                   unsigned long long cap, unsigned long long *ctr, unsigned long long ncur)
 {
-    const KpTables &tb = *tab;
     const uint16_t *srow_of_row = (const uint16_t *)(rowtab + tb.rt_srow_of_row);
     const int lane = threadIdx.x & 31;
-    const unsigned long long ncur = ctr[2 + depth];
     const unsigned long long nw = (unsigned long long)gridDim.x * (blockDim.x >> 5);
     for (unsigned long long i = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < ncur; i += nw) {
-        KpBtNode nd = cur[i];
+        KpBtNode nd;   // written by another CTA one level earlier: read at L2
+        nd.pat = __ldcg(&cur[i].pat);
+        nd.key = __ldcg(&cur[i].key);
         // location of the node; its children differ in one digit, so they are located by a delta (no divisions)
         unsigned long long ntile = 0;
         uint32_t nrow = 0, nd0 = 0;
@@ -975,6 +974,40 @@ __global__ void __launch_bounds__(256) kp_backtrack_level_kernel(const KpTables 
                 }
             }
         }
+    }
+}
+
+__global__ void __launch_bounds__(256) kp_backtrack_level_kernel(const KpTables *tab, const uint8_t *rowtab, const KpView vw,
+                                                                 int depth, const KpBtNode *cur, KpBtNode *nxt,
+                                                                 KpBtNode *leaves, unsigned long long cap,
+                                                                 unsigned long long *ctr)
+{
+    kp_backtrack_level(*tab, rowtab, vw, depth, cur, nxt, leaves, cap, ctr, ctr[2 + depth]);
+}
+
+// All depths in one launch (cooperative launch: every CTA is resident), a grid-wide barrier between depths:
+// ctr[72] counts arrivals.  Stops at the first empty frontier.
+__global__ void __launch_bounds__(256) kp_backtrack_all_kernel(const KpTables *tab, const uint8_t *rowtab, const KpView vw,
+                                                               int levels, KpBtNode *fa, KpBtNode *fb, KpBtNode *leaves,
+                                                               unsigned long long cap, unsigned long long *ctr)
+{
+    const KpTables &tb = *tab;
+    for (int d = 0; d < levels; d++) {
+        const unsigned long long ncur = __ldcg(&ctr[2 + d]);
+        if (ncur == 0) break;   // the same value in every CTA: it was final before the last barrier
+        kp_backtrack_level(tb, rowtab, vw, d, (d & 1) ? fb : fa, (d & 1) ? fa : fb, leaves, cap, ctr, ncur < cap ? ncur : cap);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            atomicAdd(&ctr[72], 1ULL);
+            const unsigned long long want = (unsigned long long)(d + 1) * gridDim.x;
+            unsigned long long seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(ctr + 72) : "memory");
+                if (seen < want) __nanosleep(100);
+            } while (seen < want);
+        }
+        __syncthreads();
     }
 }
 
