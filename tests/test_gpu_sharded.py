@@ -99,3 +99,19 @@ def test_sharded_multiprocess():
                         "NNNNANNN"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SHARDED OK" in r.stdout
+
+
+def test_cli_on_a_table_larger_than_one_gpu():
+    """The command line under torchrun on the full N^9 pattern (169 GB of scores): the final fit is sharded over the
+    ranks by itself; the CLI's own assertions check the counts of the partition against the input totals."""
+    import torch
+
+    if torch.cuda.device_count() < 2 or torch.cuda.get_device_properties(0).total_memory < 120e9:
+        pytest.skip("needs two GPUs with at least 120 GB each")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29613", os.path.join(root, "tools", "cli_n9_demo.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "rc=0" in r.stdout and "General pattern: NNNNNNNNN" in r.stdout and "loss=" in r.stdout
+
