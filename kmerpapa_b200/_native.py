@@ -3,7 +3,7 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libkpapa.so")
+LIB_PATH = os.environ.get("KP_LIBKPAPA") or os.path.join(_PKG, "libkpapa.so")   # override: A/B of experimental builds
 _lib = None
 
 

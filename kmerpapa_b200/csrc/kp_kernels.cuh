@@ -36,7 +36,16 @@
 #include "kp_math.cuh"
 #include "kp_tables.h"
 
-#define KP_MAX_WARPS 14      // tiles in flight per SM (<= 128 registers per thread)
+// Tiles in flight per SM.  Warps are allocated four at a time, so 13-16 warps leave 128 registers per thread, 12 leave
+// 170: measured 14 warps / 128 registers (spills, tight scheduling) 27.1 ms, 12 warps / 161 registers 25.4 ms, 10: 26.6,
+// 8: 29.3 (one 9-mer DP, tools/ab_libs.sh).
+#ifndef KP_MAX_WARPS
+#define KP_MAX_WARPS 12
+#endif
+#define KP_DP_BOUNDS __launch_bounds__(KP_MAX_WARPS * 32, 1)
+#ifndef KP_PIPE_DEPTH
+#define KP_PIPE_DEPTH 2      // register stages of the child-tile stream (3 needs <= 13 warps for its registers)
+#endif
 #ifndef KP_PF_DIST
 #define KP_PF_DIST 2         // L2 prefetch distance of the child-tile stream, in (32 rows x 1 split) steps
 #endif
@@ -223,7 +232,7 @@ struct KpDpParams {
 //     written and read by the same kernel, so its loads are ld.global.cg instead of the read-only (.nc) path - which
 //     costs more than the overlapped wave tails gain in a sustained run.
 template <int R0, bool WIDE, int RP, int SHARD>
-__global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const KpDpParams p)
+__global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
 {
     typedef typename KpCnt<WIDE>::type C;
     constexpr int NG = (R0 + 3) / 4;
@@ -363,6 +372,9 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
             const int nchunk = (nrows + 31) >> 5;
             const int nstep = nhs > 0 ? nchunk * nhs : 0;
             float4 xa0[NG], xb0[NG], xa1[NG], xb1[NG];
+#if KP_PIPE_DEPTH == 3
+            float4 xa2[NG], xb2[NG];
+#endif
             const float4 *tb4 = (const float4 *)tbase;
             const uint32_t stride4 = stride >> 2;                 // tile stride in float4
             int ls = 0, lrow = lane;          // split and row of the next load
@@ -424,6 +436,21 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
             us = 0; urow += 32;                                                                       \
         }                                                                                             \
     }
+#if KP_PIPE_DEPTH == 3
+            if (nstep > 0) {
+                for (int i = 0; i < p.pf_dist; i++) KP_FL_PREFETCH()
+                KP_FL_LOAD(xa0, xb0)
+                if (nstep > 1) KP_FL_LOAD(xa1, xb1)
+            }
+            for (int t = 0; t < nstep; t += 3) {   // a load is always two steps ahead of its use
+                if (t + 2 < nstep) KP_FL_LOAD(xa2, xb2)
+                KP_FL_USE(xa0, xb0)
+                if (t + 3 < nstep) KP_FL_LOAD(xa0, xb0)
+                if (t + 1 < nstep) KP_FL_USE(xa1, xb1)
+                if (t + 4 < nstep) KP_FL_LOAD(xa1, xb1)
+                if (t + 2 < nstep) KP_FL_USE(xa2, xb2)
+            }
+#else
             if (nstep > 0) {
                 for (int i = 0; i < p.pf_dist; i++) KP_FL_PREFETCH()
                 KP_FL_LOAD(xa0, xb0)
@@ -436,6 +463,7 @@ __global__ void __launch_bounds__(KP_MAX_WARPS * 32, 1) kp_dp_rows_kernel(const 
                 KP_FL_USE(xa1, xb1)
             }
             if (t < nstep) KP_FL_USE(xa0, xb0)
+#endif
 #undef KP_FL_LOAD
 #undef KP_FL_USE
 #undef KP_FL_PREFETCH
