@@ -64,6 +64,12 @@ typedef struct kp_plan_info {
     uint32_t sm_count;
 } kp_plan_info;
 
+/* Return codes.  KP_ERR_CAPACITY: the workspace `cap` the caller passed was too small for the result (kp_backtrack,
+ * kp_cv_heldout, kp_dp_cv_job, kp_shard_backtrack, kp_greedy): call again with a larger one.  Everything else is KP_ERR. */
+#define KP_OK 0
+#define KP_ERR 1
+#define KP_ERR_CAPACITY 2
+
 const char *kp_last_error(void);
 int kp_version(void);
 
@@ -118,6 +124,14 @@ int kp_split_codes(kp_plan *plan, const float *d_best, const uint16_t *d_kept, c
 int kp_gather_table(kp_plan *plan, const float *d_table, uint64_t first, uint64_t n, float *h_out, void *stream);
 /* h_out[i] = 1 if pattern first + i is kept whole. */
 int kp_gather_kept(kp_plan *plan, const uint16_t *d_kept, uint64_t first, uint64_t n, uint8_t *h_out, void *stream);
+
+/*
+ * Scores (h_best), kept-whole flags (h_kept) and split codes (h_codes, as kp_split_codes) of arbitrary patterns given by
+ * their dense numbers; any of the three outputs may be NULL.  Used by the full-size parity tests to pull whole
+ * sub-lattices (e.g. every sub-pattern of ANNNANNNN out of the NNNNANNNN table).  Synchronises.
+ */
+int kp_gather_patterns(kp_plan *plan, const float *d_table, const uint16_t *d_kept, const uint64_t *h_patnums, uint64_t n,
+                       float *h_best, uint8_t *h_kept, uint8_t *h_codes, void *stream);
 
 /*
  * One cross-validation job = one fold x alpha x penalty.  d_exp?tot: all-fold totals, d_exp?test: the fold's

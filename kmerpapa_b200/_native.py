@@ -11,6 +11,9 @@ class KpError(RuntimeError):
     pass
 
 
+KP_OK, KP_ERR, KP_ERR_CAPACITY = 0, 1, 2   # return codes of include/kmerpapa_b200.h
+
+
 class PlanInfo(ctypes.Structure):
     _fields_ = [
         ("npat", ctypes.c_uint64), ("nkmer", ctypes.c_uint64), ("ntiles", ctypes.c_uint64),
@@ -50,6 +53,7 @@ SYMBOLS = {
     "kp_split_codes": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp]),
     "kp_gather_table": (_int, [_vp, _vp, _u64, _u64, _vp, _vp]),
     "kp_gather_kept": (_int, [_vp, _vp, _u64, _u64, _vp, _vp]),
+    "kp_gather_patterns": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp]),
     "kp_dp_cv_job": (_int, [_vp, _vp, _vp, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp, _vp, _vp, _u64, _vp, _vp]),
     "kp_cv_heldout": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _u64, _vp, _u64, _vp, _vp]),
     "kp_pattern_counts": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp]),

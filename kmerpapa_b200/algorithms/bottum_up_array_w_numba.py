@@ -39,6 +39,33 @@ def _world():
     return 0, 1
 
 
+def dp_buffer_bytes(plan):
+    """Device bytes one unsharded DP allocates on top of the k-mer tables: score table, kept-whole masks, the two
+    expanded count tables and the backtrack workspace."""
+    info = plan.info
+    return (int(info.table_elems) * 4 + int(info.kept_elems) * 2 + 2 * int(info.expanded_elems) * 8
+            + int(info.backtrack_ws_bytes))
+
+
+def fits_one_gpu(plan):
+    """True when the DP's buffers fit in what is free on the plan's device right now, counting what the plan already
+    holds (its cached buffers are reused, not allocated again)."""
+    import torch
+
+    free, _total = torch.cuda.mem_get_info(plan.device)
+    held = sum(t.numel() * t.element_size() for name, t in plan._buf.items()
+               if name in ("best", "kept", "expM", "expU", "btws"))
+    reserve = 512 << 20   # allocator slack, CUDA context growth
+    return dp_buffer_bytes(plan) - held + reserve <= free + _cached_free(plan.device)
+
+
+def _cached_free(device):
+    """Bytes torch's caching allocator holds but does not use (they count as free for a new torch allocation)."""
+    import torch
+
+    return torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+
+
 def _sharded_partition(plan, eM, eU, max_count, alpha, beta, penalty, rank, world):
     """One DP over all ranks of the process group (kmerpapa_b200/sharded.py).  Returns None when this general pattern
     cannot be sharded over `world` ranks (every rank takes the same decision: it depends on the plan only)."""
@@ -49,12 +76,11 @@ def _sharded_partition(plan, eM, eU, max_count, alpha, beta, penalty, rank, worl
 
     import torch.distributed as dist
 
-    table_bytes = int(plan.info.table_elems) * 4 + int(plan.info.kept_elems) * 2
-    total = torch.cuda.get_device_properties(plan.device).total_memory
-    if table_bytes < 0.8 * total:
+    if fits_one_gpu(plan):
         # the table fits one GPU: mapping the peers' shards (CUDA IPC, 0.1-0.3 s) costs more than the one DP gains
         # (tools/shard_overhead.py); callers that run many DPs keep a ShardedDP(replicate=True) themselves
         return None
+    torch.cuda.empty_cache()   # the shards are plain cudaMalloc allocations (CUDA IPC): give them torch's cached blocks
     try:
         sh = sharded.ShardedDP(plan, rank, world, replicate=False)
     except KpError:
@@ -65,12 +91,19 @@ def _sharded_partition(plan, eM, eU, max_count, alpha, beta, penalty, rank, worl
         if sh is not None:
             sh.close()
         return None
+    # close() is collective (it must not free a table a peer's kernels still read), so every rank reaches it, also
+    # when its own part failed: the error is raised after the shards are released
+    res = err = None
     try:
         sh.connect()
         sh.run(eM, eU, max_count, alpha, beta, penalty)
-        return sh.top_score(), sh.backtrack()
-    finally:
-        sh.close()
+        res = sh.top_score(), sh.backtrack()
+    except Exception as e:   # noqa: BLE001 - re-raised below
+        err = e
+    sh.close()
+    if err is not None:
+        raise err
+    return res
 
 
 def partition_from_arrays(gen_pat, codes, pos, neg, alpha, beta, penalty, device=None, want_counts=False):
@@ -79,6 +112,7 @@ def partition_from_arrays(gen_pat, codes, pos, neg, alpha, beta, penalty, device
     Inside an NCCL process group (torchrun, one process per GPU) a DP whose table does not fit one GPU is sharded over
     the ranks (capacity mode of kmerpapa_b200/sharded.py); every rank gets the result."""
     plan = get_plan(gen_pat, device)
+    plan.release_buffers(prefix="cv")   # a cross-validation that ran before the final fit keeps nothing alive
     kM, kU = plan.pack_counts(codes, pos, neg)
     eM, eU = plan.expand(kM, kU)
     max_count = int(pos.sum()) + int(neg.sum())

@@ -12,7 +12,7 @@ import ctypes
 import numpy as np
 
 from .. import CV_tools, iupac
-from .._native import KpError, check
+from .._native import KP_ERR_CAPACITY, KpError, check
 from ..engine import _torch, get_plan
 from ..score_utils import get_betas
 
@@ -41,11 +41,10 @@ def _greedy(plan, kM, kU, alpha, beta, penalty, test=None, cap=65536):
         if rc == 0:
             k = n.value
             return pats[:k].copy(), loss[:k].copy(), (tst[:k].copy() if test else None), total.value
-        msg = plan.lib.kp_last_error().decode()
-        if "capacity" in msg and cap < (1 << 24):
+        if rc == KP_ERR_CAPACITY and cap < (1 << 24):
             cap *= 8
             continue
-        raise KpError("kp_greedy: " + msg)
+        raise KpError("kp_greedy: " + plan.lib.kp_last_error().decode())
 
 
 def greedy_partition(genpat, contextD, alpha, beta, penalty, args):

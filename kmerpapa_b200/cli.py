@@ -92,9 +92,14 @@ def _pattern_counts(gen_pat, contextD, names):
     return [(int(m), int(u)) for m, u in zip(M, U)]
 
 
-def _init_distributed():
+def _init_distributed(args=None):
     """Under torchrun (WORLD_SIZE > 1) every process takes one GPU and joins an NCCL group: the CV grid is then
-    sharded by job across the GPUs.  Returns this process's rank."""
+    sharded by job across the GPUs.  Returns this process's rank.
+
+    Every rank samples the folds itself (same RandomState stream), so all ranks need the SAME seed: without --seed the
+    reference seeds from OS entropy (RandomState(None)); here rank 0 draws that seed and broadcasts it, otherwise the
+    ranks would cross-validate on different fold samplings and could enter the final (collective) fit with different
+    parameters."""
     import os
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -107,14 +112,31 @@ def _init_distributed():
         local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    share_seed(args)
     return dist.get_rank()
+
+
+def share_seed(args):
+    """All ranks of the process group leave with the same args.seed (rank 0's; drawn from OS entropy when unset)."""
+    import torch.distributed as dist
+
+    if args is None or not dist.is_initialized() or dist.get_world_size() <= 1:
+        return
+    box = [None]
+    if dist.get_rank() == 0:
+        seed = args.seed
+        if seed is None:
+            seed = int(np.random.SeedSequence().generate_state(1)[0])   # 32 bits of OS entropy: a valid RandomState seed
+        box[0] = seed
+    dist.broadcast_object_list(box, src=0)
+    args.seed = box[0]
 
 
 def main(args=None):
     """Runs the program; returns the exit code (0 also on input errors, like the reference)."""
     parser = get_parser()
     args = parser.parse_args(args=args)
-    rank = _init_distributed()
+    rank = _init_distributed(args)
     if rank != 0:   # only rank 0 reports and writes files; the others just run their share of the CV jobs
         import os
 

@@ -19,7 +19,14 @@ thread_local std::string g_err;
 int fail(const std::string &msg)
 {
     g_err = msg;
-    return 1;
+    return KP_ERR;
+}
+
+// the caller's workspace was too small for the result: retry with a larger `cap` (a distinct code, no message parsing)
+int fail_capacity(const std::string &msg)
+{
+    g_err = msg;
+    return KP_ERR_CAPACITY;
 }
 
 #define KP_CUDA(call)                                                                         \
@@ -50,6 +57,9 @@ struct kp_plan {
     int nwarps[2] = {0, 0};  // warps (= tiles in flight) per CTA of the DP kernel [wide]
     size_t smem_optin = 0;
     bool coop_launch = false;        // the device supports cooperative launches (backtrack: all depths in one launch)
+    // tuning knobs, read from the environment ONCE, when the plan is created (tools/ab_env.py makes a plan per setting)
+    int pf_dist = KP_PF_DIST;        // KP_PF_DIST: L2 prefetch distance of the child-tile stream
+    bool one_launch = false;         // KP_ONE_LAUNCH=1: all waves in one launch
 };
 
 // the all-N tile shape (register radix 15, two N row positions: 225 rows) gets its row pitch at compile time
@@ -167,6 +177,8 @@ static int plan_create(const char *gen_pat, int device, bool lattice, kp_plan **
     }
     p->smem_optin = prop.sharedMemPerBlockOptin;
     p->coop_launch = prop.cooperativeLaunch != 0 && !getenv("KP_NO_COOP_BACKTRACK");
+    if (const char *e = getenv("KP_PF_DIST")) p->pf_dist = atoi(e);
+    if (const char *e = getenv("KP_ONE_LAUNCH")) p->one_launch = e[0] == '1';
     for (int wide = 0; wide < 2; wide++) {
         size_t fixed = 2048 + t.rt_bytes, per_warp = t.warp_smem_bytes[wide];
         int nw = fixed < p->smem_optin ? (int)((p->smem_optin - fixed) / per_warp) : 0;
@@ -333,8 +345,7 @@ static int launch_dp(kp_plan *p, bool wide, KpDpParams prm, cudaStream_t st)
     KP_CUDA(cudaMemsetAsync(p->d_counters, 0, sizeof(uint32_t) * 128, st));
     // Opt-in (KP_ONE_LAUNCH=1) for large all-N problems: ONE launch over every wave; tiles wait for their child tiles, not
     // for a kernel boundary.  Not the default: see DESIGN.md section 4.
-    const char *one = getenv("KP_ONE_LAUNCH");
-    if (p->d_tile_done && t.ntiles >= (uint64_t)8 * p->sm_count * nw && one && one[0] == '1') {
+    if (p->d_tile_done && t.ntiles >= (uint64_t)8 * p->sm_count * nw && p->one_launch) {
         KP_CUDA(cudaMemsetAsync(p->d_tile_done, 0, t.ntiles, st));
         KP_CUDA(cudaMemsetAsync(p->d_err, 0, sizeof(int), st));
         prm.tile_list = p->d_tiles;
@@ -411,8 +422,7 @@ static int dp_counts(kp_plan *p, const int64_t *d_expM, const int64_t *d_expU, c
     prm.alpha = alpha; prm.beta = beta; prm.penalty = penalty;
     prm.best = d_best;
     prm.flags = d_kept;
-    prm.pf_dist = KP_PF_DIST;
-    if (const char *e = getenv("KP_PF_DIST")) prm.pf_dist = atoi(e);   // tuning knob
+    prm.pf_dist = p->pf_dist;
     return launch_dp(p, wide, prm, (cudaStream_t)stream);
 }
 
@@ -478,7 +488,7 @@ int kp_backtrack(kp_plan *p, const float *d_best, const uint16_t *d_kept, void *
     KP_CUDA(cudaStreamSynchronize(st));
     if (herr == 2) return fail("kp_backtrack: the DP gave up waiting for a child tile (internal error)");
     *n_out = hc[0];
-    if (hc[1] || hc[0] > cap) return fail("kp_backtrack: partition larger than the workspace capacity");
+    if (hc[1] || hc[0] > cap) return fail_capacity("kp_backtrack: partition larger than the workspace capacity");
     KP_CUDA(cudaMemcpyAsync(h_patnums, sorted, hc[0] * 8, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaStreamSynchronize(st));
     return 0;
@@ -504,7 +514,8 @@ int kp_cv_heldout(kp_plan *p, const float *d_train, const uint16_t *d_kept, cons
     unsigned long long hc[2] = {0, 0};
     KP_CUDA(cudaMemcpyAsync(hc, ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaStreamSynchronize(st));
-    if (hc[1] || hc[0] > cap || hc[0] == 0) return fail("kp_cv_heldout: partition larger than the workspace capacity");
+    if (hc[1] || hc[0] > cap) return fail_capacity("kp_cv_heldout: partition larger than the workspace capacity");
+    if (hc[0] == 0) return fail("kp_cv_heldout: the backtrack produced no leaf (internal error)");
     std::vector<unsigned long long> hk(hc[0]);
     std::vector<float> hv(hc[0]);
     KP_CUDA(cudaMemcpyAsync(hk.data(), keys, hc[0] * 8, cudaMemcpyDeviceToHost, st));
@@ -527,9 +538,9 @@ int kp_dp_cv_job(kp_plan *p, const int64_t *d_expMtot, const int64_t *d_expUtot,
     if (dp_counts(p, d_expMtot, d_expUtot, d_expMtest, d_expUtest, max_count, alpha, beta_fold, penalty, d_train, d_kept, stream))
         return 1;
     if (h_top) {
-        if (kp_cv_heldout(p, d_train, d_kept, d_expMtot, d_expUtot, d_expMtest, d_expUtest, alpha, beta_fold, penalty, UINT64_MAX,
-                          d_ws, cap, h_top + 1, stream))
-            return 1;
+        if (int rc = kp_cv_heldout(p, d_train, d_kept, d_expMtot, d_expUtot, d_expMtest, d_expUtest, alpha, beta_fold, penalty,
+                                   UINT64_MAX, d_ws, cap, h_top + 1, stream))
+            return rc;
         uint64_t tile; uint32_t srow, d0;
         kp_locate(p->host, p->host.npat - 1, &tile, &srow, &d0);
         size_t top = (size_t)tile * t.tile_stride + ((size_t)(d0 >> 2) * t.rp + srow) * 4 + (d0 & 3);
@@ -590,6 +601,35 @@ int kp_gather_kept(kp_plan *p, const uint16_t *d_kept, uint64_t first, uint64_t 
     return 0;
 }
 
+// scores / kept-whole flags / split codes of arbitrary patterns of an unsharded table (any of the outputs may be null)
+int kp_gather_patterns(kp_plan *p, const float *d_table, const uint16_t *d_kept, const uint64_t *h_patnums, uint64_t n,
+                       float *h_best, uint8_t *h_kept, uint8_t *h_codes, void *stream)
+{
+    if (!p || !h_patnums) return fail("kp_gather_patterns: null argument");
+    if (!p->host.lattice) return fail("kp_gather_patterns: this plan was created without the tile lattice (kp_plan_create_lite)");
+    if ((h_best || h_codes) && !d_table) return fail("kp_gather_patterns: scores and split codes need the score table");
+    if ((h_kept || h_codes) && !d_kept) return fail("kp_gather_patterns: kept flags and split codes need the kept-whole table");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    KP_CUDA(cudaSetDevice(p->device));
+    if (scratch_reserve(p, n * 16, st)) return 1;
+    unsigned long long *d_pat = (unsigned long long *)p->d_scratch;
+    float *d_val = (float *)(d_pat + n);
+    uint8_t *d_k = (uint8_t *)(d_val + n), *d_c = d_k + n;
+    KP_CUDA(cudaMemcpyAsync(d_pat, h_patnums, n * 8, cudaMemcpyHostToDevice, st));
+    const int grid = grid_for(n, 256, p->sm_count);
+    const KpView vw = single_view(p, d_table, d_kept);
+    if (h_best) { kp_gather_kernel<<<grid, 256, 0, st>>>(p->d_tab, p->d_rowtab, vw, d_pat, 0, n, d_val); p->launches++; }
+    if (h_kept) { kp_gather_flags_kernel<<<grid, 256, 0, st>>>(p->d_tab, p->d_rowtab, vw, d_pat, 0, n, d_k); p->launches++; }
+    if (h_codes) { kp_split_codes_kernel<<<grid, 256, 0, st>>>(p->d_tab, p->d_rowtab, vw, d_pat, n, d_c); p->launches++; }
+    KP_CUDA(cudaGetLastError());
+    if (h_best) KP_CUDA(cudaMemcpyAsync(h_best, d_val, n * 4, cudaMemcpyDeviceToHost, st));
+    if (h_kept) KP_CUDA(cudaMemcpyAsync(h_kept, d_k, n, cudaMemcpyDeviceToHost, st));
+    if (h_codes) KP_CUDA(cudaMemcpyAsync(h_codes, d_c, n, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int kp_pattern_counts(kp_plan *p, const int64_t *d_kmerM, const int64_t *d_kmerU, const uint64_t *h_patnums, uint64_t n,
                       int64_t *h_M, int64_t *h_U, void *stream)
 {
@@ -601,8 +641,9 @@ int kp_pattern_counts(kp_plan *p, const int64_t *d_kmerM, const int64_t *d_kmerU
     unsigned long long *d_pat = (unsigned long long *)p->d_scratch;
     long long *d_out = (long long *)(d_pat + n);
     KP_CUDA(cudaMemcpyAsync(d_pat, h_patnums, n * 8, cudaMemcpyHostToDevice, st));
-    kp_pattern_counts_kernel<<<(int)n, 256, 0, st>>>(p->d_tab, p->host.nkmer, (const long long *)d_kmerM,
-                                                     (const long long *)d_kmerU, d_pat, d_out, d_out + n);
+    const int pc_grid = (int)std::min<uint64_t>(n, (uint64_t)p->sm_count * 16);
+    kp_pattern_counts_kernel<<<pc_grid, 256, 0, st>>>(p->d_tab, n, (const long long *)d_kmerM, (const long long *)d_kmerU,
+                                                      d_pat, d_out, d_out + n);
     p->launches++;
     KP_CUDA(cudaGetLastError());
     KP_CUDA(cudaMemcpyAsync(h_M, d_out, n * 8, cudaMemcpyDeviceToHost, st));
@@ -815,7 +856,7 @@ int kp_shard_dp_wave(kp_shard *s, int wave, const int64_t *d_expM, const int64_t
     prm.alpha = alpha; prm.beta = beta; prm.penalty = penalty;
     prm.best = s->d_best;
     prm.flags = s->d_kept;
-    prm.pf_dist = KP_PF_DIST;
+    prm.pf_dist = p->pf_dist;
     prm.view = s->view;
     prm.my_rank = s->rank;
     prm.tile_list = s->d_tiles + lo;
@@ -858,7 +899,7 @@ int kp_shard_backtrack(kp_shard *s, void *d_ws, uint64_t cap, uint64_t root, uin
     KP_CUDA(cudaMemcpyAsync(hc, ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaStreamSynchronize(st));
     *n_out = hc[0];
-    if (hc[1] || hc[0] > cap) return fail("kp_shard_backtrack: partition larger than the workspace capacity");
+    if (hc[1] || hc[0] > cap) return fail_capacity("kp_shard_backtrack: partition larger than the workspace capacity");
     KP_CUDA(cudaMemcpyAsync(h_patnums, sorted, hc[0] * 8, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaStreamSynchronize(st));
     return 0;
@@ -947,7 +988,8 @@ int kp_greedy(kp_plan *p, const int64_t *d_kmerM, const int64_t *d_kmerU, const 
     KP_CUDA(cudaMemcpyAsync(hc, ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaStreamSynchronize(st));
     *n_out = hc[0];
-    if (hc[1] || hc[0] > cap || hc[0] == 0) return fail("kp_greedy: partition larger than the workspace capacity");
+    if (hc[1] || hc[0] > cap) return fail_capacity("kp_greedy: partition larger than the workspace capacity");
+    if (hc[0] == 0) return fail("kp_greedy: no leaf (internal error)");
     std::vector<KpGreedyLeaf> hv(hc[0]);
     KP_CUDA(cudaMemcpyAsync(hv.data(), sorted, hc[0] * sizeof(KpGreedyLeaf), cudaMemcpyDeviceToHost, st));
     KP_CUDA(cudaStreamSynchronize(st));

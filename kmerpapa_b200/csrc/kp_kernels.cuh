@@ -1299,40 +1299,57 @@ __global__ void kp_gather_flags_kernel(const KpTables *tab, const uint8_t *rowta
 }
 
 // ---------------------------------------------------------------------------------------------------
-// counts of arbitrary patterns from the k-mer tables (one CTA per pattern)
+// counts of arbitrary patterns from the k-mer tables: one CTA per pattern at a time, and the CTA enumerates only the
+// k-mers the pattern matches (mixed radix over the sizes of its per-position subsets), so a whole partition costs
+// one pass over the 4^k k-mers (pattern_utils.py:192-215 walks matches() the same way, in Python)
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) kp_pattern_counts_kernel(const KpTables *tab, unsigned long long nkmer,
+__global__ void __launch_bounds__(256) kp_pattern_counts_kernel(const KpTables *tab, unsigned long long npatq,
                                                                 const long long *kmerM, const long long *kmerU,
                                                                 const unsigned long long *patnums, long long *outM,
                                                                 long long *outU)
 {
     const KpTables &tb = *tab;
-    __shared__ uint32_t masks[KP_MAXPOS];
+    __shared__ uint32_t s_n[KP_MAXPOS];          // bases in the subset of position e
+    __shared__ uint32_t s_off[KP_MAXPOS][4];     // k-mer index contribution of each of them
+    __shared__ unsigned long long s_total;
     __shared__ long long redM[256], redU[256];
-    unsigned long long pat = patnums[blockIdx.x];
-    if (threadIdx.x == 0) {
-        unsigned long long x = pat;
-        for (int e = 0; e < tb.npos; e++) { masks[e] = tb.digit_mask[e][x % tb.radix[e]]; x /= tb.radix[e]; }
-    }
-    __syncthreads();
-    long long am = 0, au = 0;
-    for (unsigned long long x = threadIdx.x; x < nkmer; x += blockDim.x) {
-        unsigned long long r = x;
-        bool in = true;
-        for (int e = 0; e < tb.npos; e++) {
-            uint32_t b = (uint32_t)(r % tb.nbase[e]);
-            r /= tb.nbase[e];
-            if (!(masks[e] & tb.digit_mask[e][b])) { in = false; break; }
+    for (unsigned long long q = blockIdx.x; q < npatq; q += gridDim.x) {
+        if (threadIdx.x == 0) {
+            unsigned long long x = patnums[q], total = 1;
+            for (int e = 0; e < tb.npos; e++) {
+                const uint32_t m = tb.digit_mask[e][x % tb.radix[e]];
+                x /= tb.radix[e];
+                uint32_t n = 0;
+                for (int b = 0; b < 4; b++)
+                    if ((m >> b) & 1u) s_off[e][n++] = (uint32_t)tb.mask_digit[e][1u << b] * tb.kw[e];
+                s_n[e] = n;
+                total *= n;
+            }
+            s_total = total;
         }
-        if (in) { am += kmerM[x]; au += kmerU[x]; }
-    }
-    redM[threadIdx.x] = am; redU[threadIdx.x] = au;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) { redM[threadIdx.x] += redM[threadIdx.x + s]; redU[threadIdx.x] += redU[threadIdx.x + s]; }
+        __syncthreads();
+        long long am = 0, au = 0;
+        const unsigned long long total = s_total;
+        for (unsigned long long j = threadIdx.x; j < total; j += blockDim.x) {
+            unsigned long long r = j;
+            uint32_t kidx = 0;
+            for (int e = 0; e < tb.npos; e++) {
+                const uint32_t n = s_n[e];
+                kidx += s_off[e][r % n];
+                r /= n;
+            }
+            am += kmerM[kidx];
+            au += kmerU[kidx];
+        }
+        redM[threadIdx.x] = am; redU[threadIdx.x] = au;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) { redM[threadIdx.x] += redM[threadIdx.x + s]; redU[threadIdx.x] += redU[threadIdx.x + s]; }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) { outM[q] = redM[0]; outU[q] = redU[0]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { outM[blockIdx.x] = redM[0]; outU[blockIdx.x] = redU[0]; }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -8,7 +8,7 @@ import ctypes
 import numpy as np
 
 from . import _native
-from ._native import KpError, check
+from ._native import KP_ERR_CAPACITY, KpError, check
 
 _PLANS = {}
 
@@ -41,6 +41,7 @@ class PartitionPlan:
         self.info = info
         self.npat, self.nkmer = int(info.npat), int(info.nkmer)
         self._buf = {}
+        self._cv_state = None
         self.top_elem = None
         if not self.lite:
             off = ctypes.c_uint64()
@@ -69,8 +70,15 @@ class PartitionPlan:
             self._buf[name] = t
         return t
 
-    def release_buffers(self):
-        self._buf.clear()
+    def release_buffers(self, prefix=None):
+        """Drop the cached device buffers (all, or those whose name starts with `prefix`)."""
+        if prefix is None:
+            self._buf.clear()
+        else:
+            for name in [n for n in self._buf if n.startswith(prefix)]:
+                del self._buf[name]
+        if prefix is None or prefix == "cv":
+            self._cv_state = None
 
     @property
     def launches(self):
@@ -128,6 +136,7 @@ class PartitionPlan:
 
     # -- K5: backtrack ---------------------------------------------------------------------------
     TOP = (1 << 64) - 1
+    MAX_CAP = 1 << 26   # largest backtrack workspace (in leaves) the capacity retries grow to
 
     def backtrack(self, best, kept, cap=65536, root=None):
         """Dense pattern numbers of the optimal partition of `root` (default: the general pattern) in the
@@ -141,11 +150,10 @@ class PartitionPlan:
                                        self.TOP if root is None else int(root), out.ctypes.data, ctypes.byref(n), self._stream())
             if rc == 0:
                 return out[: n.value].copy()
-            msg = self.lib.kp_last_error().decode()
-            if "capacity" in msg and cap < (1 << 26):
+            if rc == KP_ERR_CAPACITY and cap < self.MAX_CAP:
                 cap *= 8
                 continue
-            raise KpError("kp_backtrack: " + msg)
+            raise KpError("kp_backtrack: " + self.lib.kp_last_error().decode())
 
     def split_codes(self, best, kept, patnums):
         """The reference's backtrack pointer as position*8+split codes (0xFF: kept whole)."""
@@ -173,11 +181,10 @@ class PartitionPlan:
                                        ctypes.cast(top, ctypes.c_void_p) if read_top else None, self._stream())
             if rc == 0:
                 break
-            msg = self.lib.kp_last_error().decode()
-            if "capacity" in msg and cap < (1 << 26):
+            if rc == KP_ERR_CAPACITY and cap < self.MAX_CAP:
                 cap *= 8
                 continue
-            raise KpError("kp_dp_cv_job: " + msg)
+            raise KpError("kp_dp_cv_job: " + self.lib.kp_last_error().decode())
         self._cv_state = (eMtot, eUtot, eMte, eUte, float(alpha), float(beta), float(penalty))
         if not read_top:
             return train, kept
@@ -186,13 +193,21 @@ class PartitionPlan:
     def cv_heldout(self, root, cap=65536):
         """Held-out loss of the best partition of pattern `root` for the last cv_job (reference: test_score_mem[root])."""
         torch = _torch()
+        if self._cv_state is None:
+            raise KpError("cv_heldout: no cv_job has run on this plan yet")
         eMtot, eUtot, eMte, eUte, alpha, beta, penalty = self._cv_state
-        ws = self._buffer("btws", int(self.lib.kp_backtrack_ws_bytes(cap)), torch.uint8)
         out = ctypes.c_float(0)
-        check(self.lib.kp_cv_heldout(self.handle, self._buf["cvtrain"].data_ptr(), self._buf["cvkept"].data_ptr(),
-                                     eMtot.data_ptr(), eUtot.data_ptr(), eMte.data_ptr(), eUte.data_ptr(), alpha, beta, penalty,
-                                     int(root), ws.data_ptr(), cap, ctypes.byref(out), self._stream()), "kp_cv_heldout")
-        return np.float32(out.value)
+        while True:
+            ws = self._buffer("btws", int(self.lib.kp_backtrack_ws_bytes(cap)), torch.uint8)
+            rc = self.lib.kp_cv_heldout(self.handle, self._buf["cvtrain"].data_ptr(), self._buf["cvkept"].data_ptr(),
+                                        eMtot.data_ptr(), eUtot.data_ptr(), eMte.data_ptr(), eUte.data_ptr(), alpha, beta, penalty,
+                                        int(root), ws.data_ptr(), cap, ctypes.byref(out), self._stream())
+            if rc == 0:
+                return np.float32(out.value)
+            if rc == KP_ERR_CAPACITY and cap < self.MAX_CAP:
+                cap *= 8
+                continue
+            raise KpError("kp_cv_heldout: " + self.lib.kp_last_error().decode())
 
     # -- output stage ----------------------------------------------------------------------------
     def pattern_counts(self, kM, kU, patnums):
@@ -211,6 +226,23 @@ class PartitionPlan:
         check(self.lib.kp_gather_table(self.handle, table.data_ptr(), int(first), int(n), out.ctypes.data, self._stream()),
               "kp_gather_table")
         return out
+
+    def gather_patterns(self, table, kept, patnums, best=True, flags=False, codes=False, chunk=1 << 25):
+        """Scores / kept-whole flags / split codes of arbitrary patterns (dense numbers), pulled in chunks.
+        Returns the requested arrays in the order (best, flags, codes)."""
+        patnums = np.ascontiguousarray(patnums, dtype=np.uint64)
+        n = patnums.size
+        ob = np.empty(n, dtype=np.float32) if best else None
+        of = np.empty(n, dtype=np.uint8) if flags else None
+        oc = np.empty(n, dtype=np.uint8) if codes else None
+        for lo in range(0, n, chunk):
+            m = min(chunk, n - lo)
+            check(self.lib.kp_gather_patterns(
+                self.handle, table.data_ptr() if table is not None else None, kept.data_ptr() if kept is not None else None,
+                patnums[lo:].ctypes.data, m, ob[lo:].ctypes.data if best else None, of[lo:].ctypes.data if flags else None,
+                oc[lo:].ctypes.data if codes else None, self._stream()), "kp_gather_patterns")
+        out = tuple(x for x in (ob, of, oc) if x is not None)
+        return out[0] if len(out) == 1 else out
 
     def gather_kept(self, kept, first=0, n=None):
         n = self.npat - first if n is None else n

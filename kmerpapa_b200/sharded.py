@@ -16,7 +16,7 @@ import ctypes
 import numpy as np
 
 from . import _native
-from ._native import KpError, check
+from ._native import KP_ERR_CAPACITY, KpError, check
 from .engine import _torch
 
 
@@ -49,17 +49,40 @@ class ShardedDP:
         self._group = None
         self._token = None
 
+    def close_peers(self):
+        """Unmap the peers' shards (CUDA IPC).  Local only; see close()."""
+        for ptr in self._opened:
+            self.lib.kp_ipc_close(self.plan.device_index, ctypes.c_void_p(ptr))
+        self._opened = []
+
     def close(self):
-        if getattr(self, "handle", None):
-            for ptr in self._opened:
-                self.lib.kp_ipc_close(self.plan.device_index, ctypes.c_void_p(ptr))
-            self._opened = []
-            self.lib.kp_shard_destroy(self.handle)
-            self.handle = None
+        """Release the shard.  With peers in other processes (connect()), this is a COLLECTIVE: every rank must call
+        it.  A peer's kernels (backtrack, gather) may still be reading this rank's exported tables, and
+        freeing an allocation that another process has mapped is undefined, so the order is: drain this rank's stream,
+        wait for everyone, unmap the peers' tables, wait again, and only then free what this rank exported."""
+        if not getattr(self, "handle", None):
+            return
+        collective = self._token is not None
+        if collective:
+            import torch.distributed as dist
+
+            _torch().cuda.synchronize(self.plan.device)
+            dist.barrier(group=self._group)
+        self.close_peers()
+        if collective:
+            import torch.distributed as dist
+
+            dist.barrier(group=self._group)
+            self._token = None
+        self.lib.kp_shard_destroy(self.handle)
+        self.handle = None
 
     def __del__(self):
-        try:
-            self.close()
+        try:   # no collective from a finaliser: unmap, then free (callers that share shards across processes call close())
+            if getattr(self, "handle", None):
+                self.close_peers()
+                self.lib.kp_shard_destroy(self.handle)
+                self.handle = None
         except Exception:
             pass
 
@@ -123,11 +146,10 @@ class ShardedDP:
                                              out.ctypes.data, ctypes.byref(n), self.plan._stream())
             if rc == 0:
                 return out[: n.value].copy()
-            msg = self.lib.kp_last_error().decode()
-            if "capacity" in msg and cap < (1 << 26):
+            if rc == KP_ERR_CAPACITY and cap < self.plan.MAX_CAP:
                 cap *= 8
                 continue
-            raise KpError("kp_shard_backtrack: " + msg)
+            raise KpError("kp_shard_backtrack: " + self.lib.kp_last_error().decode())
 
     def gather(self, patnums, codes=False):
         """(scores, kept-whole flags[, split codes]) of arbitrary patterns, wherever they are stored."""

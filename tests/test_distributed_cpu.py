@@ -97,3 +97,41 @@ def test_cv_grid_sharded_over_two_ranks_matches_single_process(oracle):
     ref = oracle.cv_grid(GEN_PAT, M, U, ALPHAS, PENS, NF, SEED, nthreads=1)
     a, c, best = cv.select_best(ALPHAS, PENS, single, 1, NF, len(GEN_PAT))
     assert (a, c) == (ref["best"][0], ref["best"][1]) and np.float32(best) == np.float32(ref["best"][2])
+
+
+def _seed_worker(rank, world, port, q, seed):
+    import argparse
+
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from kmerpapa_b200 import cli
+
+    args = argparse.Namespace(seed=seed if rank == 0 else (None if seed is None else seed + 17))
+    cli.share_seed(args)
+    q.put((rank, args.seed))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("seed", [None, 5])
+def test_ranks_share_one_seed(seed):
+    """Without --seed every rank would seed its fold sampler from OS entropy and cross-validate on different folds:
+    rank 0's seed (drawn when unset) is broadcast."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000 + (0 if seed is None else 1)
+    procs = [ctx.Process(target=_seed_worker, args=(r, 2, port, q, seed)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0] == got[1] and isinstance(got[0], int)
+    if seed is not None:
+        assert got[0] == seed
+    np.random.RandomState(got[0])   # a valid legacy seed

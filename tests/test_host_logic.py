@@ -216,3 +216,34 @@ def test_no_cpu_fallback_without_gpu():
     src = "".join(open(os.path.join(dp, f)).read() for dp, _, fs in os.walk(os.path.join(ROOT, "kmerpapa_b200"))
                   for f in fs if f.endswith(".py"))
     assert "oracle" not in src.replace("no CPU", ""), "product code must not reference the oracle"
+
+
+def test_sublattice_helpers_against_the_string_enumeration():
+    from fullsize_util import sub_kmer_select, sublattice_patnums
+    from kmerpapa_b200 import iupac
+
+    gen, sub = "NRANY", "SAAKY"
+    PE, PS = iupac.PatternEnumeration(gen), iupac.PatternEnumeration(sub)
+    want = np.array([PE.pattern2num(PS.num2pattern(i)) for i in range(PS.npat)], dtype=np.uint64)
+    assert np.array_equal(sublattice_patnums(gen, sub), want)
+    kf = iupac.matches(gen)
+    assert [kf[i] for i in sub_kmer_select(gen, sub)] == iupac.matches(sub)
+
+
+def test_a_sublattice_is_a_dp_of_its_own(oracle):
+    """The premise of the full-size parity tests, checked on the oracle alone: the table of the sub-patterns of S
+    (scores and split decisions) sits verbatim inside the table of any general pattern that contains S."""
+    from fullsize_util import sub_kmer_select, sublattice_patnums
+
+    gen = "NNANN"
+    rng = np.random.default_rng(11)
+    U = 1 + rng.negative_binomial(2, 2 / (2 + 800.0), size=256)
+    M = rng.binomial(U, 0.05)
+    full = oracle.single_dp(gen, M, U, 0.7, 30.0, 3.0)
+    for sub in ("ANANN", "NNANT", "SKACN"):
+        sel = sub_kmer_select(gen, sub)
+        ref = oracle.single_dp(sub, M[sel], U[sel], 0.7, 30.0, 3.0)
+        nums = sublattice_patnums(gen, sub).astype(np.int64)
+        assert np.array_equal(full["score"][nums].view(np.uint32), ref["score"].view(np.uint32))
+        assert np.array_equal(full["split"][nums], ref["split"])
+        assert np.array_equal(full["M"][nums], ref["M"])

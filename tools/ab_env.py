@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Interleaved A/B of one environment knob of the DP (read at every kp_dp_single call):
+"""Interleaved A/B of one environment knob of the DP (knobs are read once, at plan creation: one plan per setting):
 python tools/ab_env.py NAME VALUE_A VALUE_B [gen_pat] [reps]   ('-' = unset)"""
 import os
 import sys
@@ -9,13 +9,20 @@ import numpy as np
 import torch
 
 from kmerpapa_b200 import synthetic
-from kmerpapa_b200.engine import get_plan
+from kmerpapa_b200.engine import PartitionPlan
 
 name, va, vb = sys.argv[1:4]
 gen_pat = sys.argv[4] if len(sys.argv) > 4 else "NNNNANNNN"
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 30
 kmers, pos, neg = synthetic.negbin_counts(gen_pat, 9003)
-plan = get_plan(gen_pat, 0)
+plans = []
+for v in (va, vb):
+    if v == "-":
+        os.environ.pop(name, None)
+    else:
+        os.environ[name] = v
+    plans.append(PartitionPlan(gen_pat, 0))
+plan = plans[0]
 kM, kU = plan.pack_counts(synthetic.codes_of(kmers), pos, neg)
 eM, eU = plan.expand(kM, kU)
 mc = int(pos.sum() + neg.sum())
@@ -23,15 +30,10 @@ mu = int(pos.sum()) / mc
 res = {0: [], 1: []}
 for rep in range(reps + 4):
     mode = rep & 1
-    v = vb if mode else va
-    if v == "-":
-        os.environ.pop(name, None)
-    else:
-        os.environ[name] = v
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    plan.dp_single(eM, eU, mc, 1.0, (1 - mu) / mu, 6.0)
+    plans[mode].dp_single(eM, eU, mc, 1.0, (1 - mu) / mu, 6.0)
     e1.record()
     torch.cuda.synchronize()
     if rep >= 4:
