@@ -164,6 +164,8 @@ int kp_pattern_offset(const kp_plan *plan, uint64_t patnum, uint64_t *table_elem
 
 /* Number of kernel launches issued through this plan so far (for bench.py's gpu_launches). */
 uint64_t kp_plan_launch_count(const kp_plan *plan);
+/* Name of the kernel family kp_dp_single / kp_dp_cv_job launch for this plan (reports, bench.py's roofline.kernel). */
+const char *kp_dp_kernel_name(const kp_plan *plan);
 
 /* ---------------------------------------------------------------------------------------------------
  * One DP sharded over the GPUs of a node (pattern-space sharding; the reference has no

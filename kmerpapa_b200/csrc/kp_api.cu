@@ -243,6 +243,12 @@ int kp_plan_get_info(const kp_plan *p, kp_plan_info *o)
 
 uint64_t kp_plan_launch_count(const kp_plan *p) { return p ? p->launches : 0; }
 
+const char *kp_dp_kernel_name(const kp_plan *p)
+{
+    (void)p;
+    return "kp_dp_rows_kernel";
+}
+
 int kp_pattern_offset(const kp_plan *p, uint64_t patnum, uint64_t *table_elem, uint64_t *kept_elem, uint32_t *kept_bit)
 {
     if (p && !p->host.lattice) return fail("kp_pattern_offset: this plan was created without the tile lattice (kp_plan_create_lite)");

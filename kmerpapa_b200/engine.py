@@ -80,6 +80,10 @@ class PartitionPlan:
         if prefix is None or prefix == "cv":
             self._cv_state = None
 
+    def dp_kernel_name(self):
+        """Name of the kernel family kp_dp_single / kp_dp_cv_job launch for this plan (for reports)."""
+        return self.lib.kp_dp_kernel_name(self.handle).decode()
+
     @property
     def launches(self):
         return int(self.lib.kp_plan_launch_count(self.handle))
