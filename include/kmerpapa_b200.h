@@ -148,6 +148,20 @@ int kp_dp_cv_job(kp_plan *plan, const int64_t *d_expMtot, const int64_t *d_expUt
                  float *d_train, uint16_t *d_kept, void *d_ws, uint64_t cap, float *h_top, void *stream);
 
 /*
+ * The same job without a host round trip, for callers that keep the GPU busy with the next job while this one's results
+ * travel: kp_cv_job_enqueue queues the DP, the backtrack, the leaf kernel and the copies of their results into h_stage
+ * (page-locked host memory of kp_cv_stage_bytes(cap) bytes) and returns without synchronising; kp_cv_job_finish, called
+ * once the stream has passed that point (e.g. after an event recorded behind the call), does the host part and fills
+ * h_top[2] = (train, held-out) loss of the general pattern.  d_train / d_kept must not be overwritten before the
+ * stream has passed the enqueue (two tables in rotation suffice: work on one stream runs in order).
+ */
+uint64_t kp_cv_stage_bytes(uint64_t cap);
+int kp_cv_job_enqueue(kp_plan *plan, const int64_t *d_expMtot, const int64_t *d_expUtot, const int64_t *d_expMtest,
+                      const int64_t *d_expUtest, uint64_t max_count, double alpha, double beta_fold, double penalty,
+                      float *d_train, uint16_t *d_kept, void *d_ws, uint64_t cap, void *h_stage, void *stream);
+int kp_cv_job_finish(const void *h_stage, uint64_t cap, float *h_top);
+
+/*
  * Held-out loss of the best partition of pattern `root` after kp_dp_cv_job (the reference's test_score_mem[root],
  * bottum_up_array_penalty_plus_pseudo_CV.py:46-51, :71-78), same total / held-out tables as the job.  Synchronises.
  */

@@ -55,6 +55,9 @@ SYMBOLS = {
     "kp_gather_kept": (_int, [_vp, _vp, _u64, _u64, _vp, _vp]),
     "kp_gather_patterns": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp]),
     "kp_dp_cv_job": (_int, [_vp, _vp, _vp, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp, _vp, _vp, _u64, _vp, _vp]),
+    "kp_cv_stage_bytes": (_u64, [_u64]),
+    "kp_cv_job_enqueue": (_int, [_vp, _vp, _vp, _vp, _vp, _u64, _dbl, _dbl, _dbl, _vp, _vp, _vp, _u64, _vp, _vp]),
+    "kp_cv_job_finish": (_int, [_vp, _u64, _vp]),
     "kp_cv_heldout": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _u64, _vp, _u64, _vp, _vp]),
     "kp_pattern_counts": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp]),
     "kp_pattern_offset": (_int, [_vp, _u64, ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(ctypes.c_uint32)]),

@@ -118,6 +118,7 @@ class GpuFoldRunner:
         kM, kU = self.plan.pack_counts(codes, pos, neg, name="cvtot_k")
         self.tot = self.plan.expand(kM, kU, name="cvtot_e")
         self.folds = {}
+        self.pending = []
 
     def set_folds(self, Mf, Uf):
         self.Mf, self.Uf = Mf, Uf
@@ -142,6 +143,31 @@ class GpuFoldRunner:
         eMte, eUte = self._fold(f)
         return self.plan.cv_job(self.tot[0], self.tot[1], eMte, eUte, self.max_count, alpha, beta, penalty)
 
+    # pipelined interface: the next job's DP is queued before the previous job's results are read back, so the GPU
+    # does not idle during the host round trip (backtrack results, float32 tree sum) of every job
+    DEPTH = 2
+
+    def submit(self, tag, f, alpha, beta, penalty):
+        """Queue a job; returns the (tag, train, held-out) results that became due (oldest first)."""
+        eMte, eUte = self._fold(f)
+        self.pending.append((tag, self.plan.cv_job_submit(self.tot[0], self.tot[1], eMte, eUte, self.max_count, alpha, beta,
+                                                          penalty)))
+        out = []
+        while len(self.pending) >= self.DEPTH:
+            out.append(self._pop())
+        return out
+
+    def flush(self):
+        out = []
+        while self.pending:
+            out.append(self._pop())
+        return out
+
+    def _pop(self):
+        tag, ticket = self.pending.pop(0)
+        tr, te = self.plan.cv_job_result(ticket)
+        return tag, tr, te
+
     @property
     def device(self):
         return self.plan.device
@@ -165,6 +191,20 @@ def run_grid(gen_pat, kmers, codes, pos, neg, alphas, penalties, nfolds, nit, se
     local = np.zeros((hi - lo, 2), dtype=np.float32)
     cover = covering_patterns_per_kmer(gen_pat)
     prev_M = prev_U = None
+    pipelined = hasattr(runner, "submit")
+
+    def run_job(slot, f, alpha, beta, penalty):
+        if pipelined:   # results arrive a job or two later; the GPU already has the next DP queued by then
+            for tag, tr, te in runner.submit(slot, f, alpha, beta, penalty):
+                local[tag, 0], local[tag, 1] = tr, te
+        else:
+            local[slot, 0], local[slot, 1] = runner.run(f, alpha, beta, penalty)
+
+    def drain():
+        if pipelined:
+            for tag, tr, te in runner.flush():
+                local[tag, 0], local[tag, 1] = tr, te
+
     for it in range(nit):
         if verbosity > 0 and nit > 1:
             print("CV Iteration", it, file=sys.stderr)
@@ -208,9 +248,9 @@ def run_grid(gen_pat, kmers, codes, pos, neg, alphas, penalties, nfolds, nit, se
                 while j < jhi and jobs[j][1] == f:
                     _, _, a_i, p_i = jobs[j]
                     beta = get_betas(alphas[a_i], Mtr, Utr)[0]
-                    tr, te = runner.run(f, alphas[a_i], beta, penalties[p_i])
-                    local[j - lo, 0], local[j - lo, 1] = tr, te
+                    run_job(j - lo, f, alphas[a_i], beta, penalties[p_i])
                     j += 1
+            drain()
             th.join()
             prev_M, prev_U = cur_M, cur_U
             if verbosity > 0:
@@ -238,8 +278,8 @@ def run_grid(gen_pat, kmers, codes, pos, neg, alphas, penalties, nfolds, nit, se
         runner.set_folds(Mf, Uf)
         for j in range(jlo, jhi):
             _, f, a_i, p_i = jobs[j]
-            tr, te = runner.run(f, alphas[a_i], betas[a_i][f], penalties[p_i])
-            local[j - lo, 0], local[j - lo, 1] = tr, te
+            run_job(j - lo, f, alphas[a_i], betas[a_i][f], penalties[p_i])
+        drain()
         if progress is not None and world == 1:
             progress(it, local.reshape(nit, nfolds, na, npen, 2)[it])
     full = gather_job_results(local, len(jobs), rank, world, gather_device).reshape(nit, nfolds, na, npen, 2)

@@ -10,6 +10,7 @@
 
 #include "../../include/kmerpapa_b200.h"
 #include "kp_kernels.cuh"
+#include "kp_fiber.cuh"
 #include "kp_plan.h"
 
 namespace {
@@ -58,12 +59,22 @@ struct kp_plan {
     size_t smem_optin = 0;
     bool coop_launch = false;        // the device supports cooperative launches (backtrack: all depths in one launch)
     // tuning knobs, read from the environment ONCE, when the plan is created (tools/ab_env.py makes a plan per setting)
+    // fiber kernel (kp_fiber.cuh): tables and the fiber list, when the general pattern has the shape for it
+    KpFiberTables *d_ftab = nullptr;
+    uint8_t *d_fiberblob = nullptr;
+    uint32_t *d_fibers = nullptr;
+    size_t fiber_smem[2] = {0, 0};
+    int fiber_dbg = 0;               // KP_FIBER_DBG: timing experiments (results are wrong when set)
+    bool use_fiber = false;          // KP_DP_KERNEL=fiber|rows: which kernel family runs the unsharded DP
     int pf_dist = KP_PF_DIST;        // KP_PF_DIST: L2 prefetch distance of the child-tile stream
     bool one_launch = false;         // KP_ONE_LAUNCH=1: all waves in one launch
 };
 
 // the all-N tile shape (register radix 15, two N row positions: 225 rows) gets its row pitch at compile time
 #define KP_RP_NN 232
+#ifndef KP_FIBER_DEFAULT
+#define KP_FIBER_DEFAULT false   // which kernel family runs the unsharded DP when KP_DP_KERNEL is not set
+#endif
 
 template <bool WIDE>
 static const void *dp_kernel_for_radix(int r0, int rp)
@@ -176,6 +187,24 @@ static int plan_create(const char *gen_pat, int device, bool lattice, kp_plan **
         KP_CUDA(cudaMalloc(&p->d_tile_done, tw.size()));
     }
     p->smem_optin = prop.sharedMemPerBlockOptin;
+    if (p->host.ft.ok) {
+        const KpFiberTables &f = p->host.ft;
+        KP_CUDA(cudaMalloc(&p->d_ftab, sizeof(KpFiberTables)));
+        KP_CUDA(cudaMemcpy(p->d_ftab, &f, sizeof(KpFiberTables), cudaMemcpyHostToDevice));
+        KP_CUDA(cudaMalloc(&p->d_fiberblob, p->host.fibertab.size()));
+        KP_CUDA(cudaMemcpy(p->d_fiberblob, p->host.fibertab.data(), p->host.fibertab.size(), cudaMemcpyHostToDevice));
+        KP_CUDA(cudaMalloc(&p->d_fibers, sizeof(uint32_t) * (p->host.fiber_order.size() + 1)));
+        KP_CUDA(cudaMemcpy(p->d_fibers, p->host.fiber_order.data(), sizeof(uint32_t) * p->host.fiber_order.size(), cudaMemcpyHostToDevice));
+        for (int wide = 0; wide < 2; wide++) {
+            const size_t need = kp_fiber_smem(f.ft_bytes, f.maxhs, t.tile_kmers, wide != 0).total;
+            p->fiber_smem[wide] = need <= p->smem_optin ? need : 0;
+        }
+        KP_CUDA(cudaFuncSetAttribute((const void *)kp_dp_fiber_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+        KP_CUDA(cudaFuncSetAttribute((const void *)kp_dp_fiber_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+        p->use_fiber = KP_FIBER_DEFAULT;
+        if (const char *e = getenv("KP_DP_KERNEL")) p->use_fiber = strcmp(e, "fiber") == 0;
+        if (const char *e = getenv("KP_FIBER_DBG")) p->fiber_dbg = atoi(e);
+    }
     p->coop_launch = prop.cooperativeLaunch != 0 && !getenv("KP_NO_COOP_BACKTRACK");
     if (const char *e = getenv("KP_PF_DIST")) p->pf_dist = atoi(e);
     if (const char *e = getenv("KP_ONE_LAUNCH")) p->one_launch = e[0] == '1';
@@ -207,6 +236,9 @@ int kp_plan_destroy(kp_plan *p)
     cudaFree(p->d_counters);
     cudaFree(p->d_tile_wave);
     cudaFree(p->d_tile_done);
+    cudaFree(p->d_ftab);
+    cudaFree(p->d_fiberblob);
+    cudaFree(p->d_fibers);
     cudaFree(p->d_scratch);
     delete p;
     return 0;
@@ -245,8 +277,7 @@ uint64_t kp_plan_launch_count(const kp_plan *p) { return p ? p->launches : 0; }
 
 const char *kp_dp_kernel_name(const kp_plan *p)
 {
-    (void)p;
-    return "kp_dp_rows_kernel";
+    return p && p->use_fiber && p->fiber_smem[0] ? "kp_dp_fiber_kernel" : "kp_dp_rows_kernel";
 }
 
 int kp_pattern_offset(const kp_plan *p, uint64_t patnum, uint64_t *table_elem, uint64_t *kept_elem, uint32_t *kept_bit)
@@ -349,6 +380,31 @@ static int launch_dp(kp_plan *p, bool wide, KpDpParams prm, cudaStream_t st)
     const KpTables &t = p->host.t;
     if (nhl > 64) return fail("too many tile waves");
     KP_CUDA(cudaMemsetAsync(p->d_counters, 0, sizeof(uint32_t) * 128, st));
+    if (p->use_fiber && p->fiber_smem[wide]) {
+        // a fourth position on chip: one CTA per fiber (15 tiles), waves over the other high positions
+        KpFiberParams fp;
+        memset(&fp, 0, sizeof fp);
+        fp.tab = p->d_tab; fp.ftab = p->d_ftab; fp.fiberblob = p->d_fiberblob;
+        fp.e0 = prm.e0; fp.e1 = prm.e1; fp.s0 = prm.s0; fp.s1 = prm.s1;
+        fp.alpha = prm.alpha; fp.beta = prm.beta; fp.penalty = prm.penalty;
+        fp.best = prm.best; fp.flags = prm.flags;
+        fp.dbg = p->fiber_dbg;
+        const size_t nfl = p->host.fl_off.size() - 1;
+        for (size_t l = 0; l < nfl; l++) {
+            const uint64_t lo = p->host.fl_off[l], hi = p->host.fl_off[l + 1];
+            if (hi == lo) continue;
+            fp.fiber_list = p->d_fibers + lo;
+            fp.nfibers_wave = (uint32_t)(hi - lo);
+            fp.counter = p->d_counters + l;
+            fp.leaf_wave = (l == 0);
+            const int grid = (int)std::min<uint64_t>(hi - lo, (uint64_t)p->sm_count);
+            if (wide) kp_dp_fiber_kernel<true><<<grid, KP_FIBER_THREADS, p->fiber_smem[1], st>>>(fp);
+            else kp_dp_fiber_kernel<false><<<grid, KP_FIBER_THREADS, p->fiber_smem[0], st>>>(fp);
+            p->launches++;
+        }
+        KP_CUDA(cudaGetLastError());
+        return 0;
+    }
     // Opt-in (KP_ONE_LAUNCH=1) for large all-N problems: ONE launch over every wave; tiles wait for their child tiles, not
     // for a kernel boundary.  Not the default: see DESIGN.md section 4.
     if (p->d_tile_done && t.ntiles >= (uint64_t)8 * p->sm_count * nw && p->one_launch) {
@@ -553,6 +609,57 @@ int kp_dp_cv_job(kp_plan *p, const int64_t *d_expMtot, const int64_t *d_expUtot,
         KP_CUDA(cudaMemcpyAsync(h_top, d_train + top, sizeof(float), cudaMemcpyDeviceToHost, st));
         KP_CUDA(cudaStreamSynchronize(st));
     }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// A CV job without a host round trip: kp_cv_job_enqueue queues the DP, the backtrack, the leaf kernel and the copies of
+// their results into a (pinned) host staging area and returns at once; kp_cv_job_finish, called after the stream has
+// passed that point (an event the caller records), does the host part (the float32 tree sum).  With two train tables
+// in rotation the next job's DP is queued before the previous job's results are read, so the GPU never waits for the host.
+// Staging layout: u64 leaves, u64 overflow, f32 train loss of the general pattern, pad to 32 bytes; u64 keys[cap]; f32 vals[cap].
+// ---------------------------------------------------------------------------------------------------
+uint64_t kp_cv_stage_bytes(uint64_t cap) { return 32 + cap * 12; }
+
+int kp_cv_job_enqueue(kp_plan *p, const int64_t *d_expMtot, const int64_t *d_expUtot, const int64_t *d_expMtest,
+                      const int64_t *d_expUtest, uint64_t max_count, double alpha, double beta_fold, double penalty,
+                      float *d_train, uint16_t *d_kept, void *d_ws, uint64_t cap, void *h_stage, void *stream)
+{
+    if (!p || !d_expMtest || !d_expUtest || !d_ws || !h_stage) return fail("kp_cv_job_enqueue: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    KP_CUDA(cudaSetDevice(p->device));
+    const KpTables &t = p->host.t;
+    if (dp_counts(p, d_expMtot, d_expUtot, d_expMtest, d_expUtest, max_count, alpha, beta_fold, penalty, d_train, d_kept, stream))
+        return 1;
+    unsigned long long *sorted, *keys, *ctr;
+    float *vals;
+    if (backtrack_device(p, single_view(p, d_train, d_kept), d_ws, cap, p->host.npat - 1, st, &sorted, &keys, &vals, &ctr)) return 1;
+    kp_cv_leaf_kernel<<<p->sm_count, 128, 0, st>>>(p->d_tab, p->d_rowtab, (const long long *)d_expMtot, (const long long *)d_expUtot,
+                                                   (const long long *)d_expMtest, (const long long *)d_expUtest, alpha, beta_fold,
+                                                   penalty, sorted, ctr, cap, vals);
+    p->launches++;
+    KP_CUDA(cudaGetLastError());
+    unsigned char *h = (unsigned char *)h_stage;
+    uint64_t tile; uint32_t srow, d0;
+    kp_locate(p->host, p->host.npat - 1, &tile, &srow, &d0);
+    const size_t top = (size_t)tile * t.tile_stride + ((size_t)(d0 >> 2) * t.rp + srow) * 4 + (d0 & 3);
+    KP_CUDA(cudaMemcpyAsync(h, ctr, 16, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaMemcpyAsync(h + 16, d_train + top, sizeof(float), cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaMemcpyAsync(h + 32, keys, cap * 8, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(cudaMemcpyAsync(h + 32 + cap * 8, vals, cap * 4, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+int kp_cv_job_finish(const void *h_stage, uint64_t cap, float *h_top)
+{
+    if (!h_stage || !h_top) return fail("kp_cv_job_finish: null argument");
+    const unsigned char *h = (const unsigned char *)h_stage;
+    unsigned long long hc[2];
+    memcpy(hc, h, 16);
+    if (hc[1] || hc[0] > cap) return fail_capacity("kp_cv_job_finish: partition larger than the workspace capacity");
+    if (hc[0] == 0) return fail("kp_cv_job_finish: the backtrack produced no leaf (internal error)");
+    memcpy(h_top, h + 16, sizeof(float));
+    h_top[1] = tree_sum((const unsigned long long *)(h + 32), (const float *)(h + 32 + cap * 8), 0, hc[0], 0);
     return 0;
 }
 

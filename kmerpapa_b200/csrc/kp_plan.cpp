@@ -288,10 +288,76 @@ int kp_build_host_plan(const char *gen_pat, KpHostPlan &P, std::string &err, boo
         t.warp_smem_bytes[wide] = (uint32_t)((b + 15) & ~(size_t)15);
     }
 
+    memset(&P.ft, 0, sizeof P.ft);
     if (!lattice) {
         t.ntiles = 0;
         P.hl_off.assign(1, 0);
         return 0;
+    }
+    // ---- fiber kernel tables: all-N tile shape (register N + two N row positions) and an N among the high positions ----
+    {
+        KpFiberTables &f = P.ft;
+        int fhi = -1;
+        for (int i = 0; i < t.nhigh && fhi < 0; i++)
+            if (t.radix[t.highpos[i]] == KP_FIBER_DIGITS) fhi = i;
+        if (t.r0 == 15 && nrows == KP_FIBER_ROWS && t.rp == 232 && rowpos.size() == 2 && fhi >= 0) {
+            f.ok = 1;
+            f.fhi = fhi;
+            f.fe = t.highpos[fhi];
+            f.hw = t.highw[f.fe];
+            f.nfibers = (uint32_t)(ntiles / KP_FIBER_DIGITS);
+            // rows in level order (stable in schedule order)
+            std::vector<int> frow_srow(nrows);
+            for (int s = 0; s < nrows; s++) frow_srow[s] = s;
+            std::stable_sort(frow_srow.begin(), frow_srow.end(), [&](int a, int b) { return level[order[a]] < level[order[b]]; });
+            std::vector<int> frow_of_srow(nrows);
+            for (int fr = 0; fr < nrows; fr++) frow_of_srow[frow_srow[fr]] = fr;
+            int maxlvl = 0;
+            for (int r = 0; r < nrows; r++) maxlvl = std::max(maxlvl, level[r]);
+            if (maxlvl != KP_FIBER_ROW_LEVELS - 1) { err = "internal: fiber row levels"; return 9; }
+            for (int l = 0; l <= KP_FIBER_ROW_LEVELS; l++) f.lvl_start[l] = 0;
+            for (int r = 0; r < nrows; r++) f.lvl_start[level[r] + 1]++;
+            for (int l = 0; l < KP_FIBER_ROW_LEVELS; l++) f.lvl_start[l + 1] += f.lvl_start[l];
+            std::vector<uint8_t> &B = P.fibertab;
+            B.clear();
+            auto align = [&](size_t a) { while (B.size() % a) B.push_back(0); };
+            auto put16 = [&](uint32_t v) { B.push_back((uint8_t)(v & 0xFF)); B.push_back((uint8_t)((v >> 8) & 0xFF)); };
+            f.ft_srow_of_frow = (uint32_t)B.size();
+            for (int fr = 0; fr < nrows; fr++) B.push_back((uint8_t)frow_srow[fr]);
+            align(4);
+            f.ft_frow_of_srow = (uint32_t)B.size();
+            for (int s = 0; s < t.rp; s++) B.push_back(s < nrows ? (uint8_t)frow_of_srow[s] : (uint8_t)0xFF);
+            align(4);
+            f.ft_xs_off = (uint32_t)B.size();
+            {
+                uint32_t o = 0;
+                for (int fr = 0; fr < nrows; fr++) { put16(o); o += (uint32_t)xsplit[order[frow_srow[fr]]].size(); }
+                put16(o);
+            }
+            align(4);
+            f.ft_xs = (uint32_t)B.size();
+            for (int fr = 0; fr < nrows; fr++)
+                for (auto &pr : xsplit[order[frow_srow[fr]]]) {
+                    const int c1 = frow_of_srow[P.srow_of_row[pr.first]], c2 = frow_of_srow[P.srow_of_row[pr.second]];
+                    if (c1 >= fr || c2 >= fr) { err = "internal: fiber row order"; return 9; }
+                    put16((uint32_t)c1 | ((uint32_t)c2 << 8));
+                }
+            align(4);
+            f.ft_bs_off = (uint32_t)B.size();
+            {
+                uint32_t o = 0;
+                for (int fr = 0; fr < nrows; fr++) { put16(o); o += (uint32_t)bases[order[frow_srow[fr]]].size(); }
+                put16(o);
+            }
+            align(4);
+            f.ft_bs = (uint32_t)B.size();
+            for (int fr = 0; fr < nrows; fr++)
+                for (uint16_t b : bases[order[frow_srow[fr]]]) B.push_back((uint8_t)b);
+            align(16);
+            f.ft_bytes = (uint32_t)B.size();
+            f.maxhs = (uint32_t)((7 * (t.nhigh - 1) + 3) & ~3);
+            if (f.maxhs < 4) f.maxhs = 4;
+        }
     }
     // ---- tiles sorted by high level ----
     int nhl = 1;
@@ -314,6 +380,20 @@ int kp_build_host_plan(const char *gen_pat, KpHostPlan &P, std::string &err, boo
     {
         std::vector<uint64_t> cur(P.hl_off.begin(), P.hl_off.end() - 1);
         for (uint64_t tile = 0; tile < ntiles; tile++) P.tile_order[cur[tl[tile]]++] = (uint32_t)tile;
+    }
+    if (P.ft.ok) {   // fibers (their digit-0 tile) by wave = level over the other high positions; a digit-0 tile has that level
+        const KpFiberTables &f = P.ft;
+        const int nfl = nhl - 3;
+        std::vector<uint64_t> cnt((size_t)nfl + 1, 0);
+        for (uint64_t tile = 0; tile < ntiles; tile++)
+            if ((tile / f.hw) % KP_FIBER_DIGITS == 0) cnt[(size_t)tl[tile] + 1]++;
+        for (int l = 0; l < nfl; l++) cnt[(size_t)l + 1] += cnt[(size_t)l];
+        P.fl_off = cnt;
+        P.fiber_order.resize(cnt[(size_t)nfl]);
+        std::vector<uint64_t> cur(cnt.begin(), cnt.end() - 1);
+        for (uint64_t tile = 0; tile < ntiles; tile++)
+            if ((tile / f.hw) % KP_FIBER_DIGITS == 0) P.fiber_order[cur[tl[tile]]++] = (uint32_t)tile;
+        if (P.fiber_order.size() != f.nfibers) { err = "internal: fiber count"; return 9; }
     }
     return 0;
 }

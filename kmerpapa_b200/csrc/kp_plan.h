@@ -19,6 +19,11 @@ struct KpHostPlan {
     uint8_t gen_mask[KP_MAXK];         // nucleotide subset of every string position (fixed ones too)
     uint8_t eff_of_pos[KP_MAXK];       // string position -> effective position index, 0xFF if fixed
     bool lattice = true;               // false: no tile lattice (tile_order / hl_off empty, the DP entry points refuse)
+    // fiber kernel (kp_fiber.cuh): tables, and the fibers (tile id of their digit-0 tile) sorted by (fiber wave, id)
+    KpFiberTables ft;
+    std::vector<uint8_t> fibertab;
+    std::vector<uint32_t> fiber_order;
+    std::vector<uint64_t> fl_off;      // offsets of the fiber waves in fiber_order
 };
 
 // Returns 0 on success; on failure fills err.

@@ -65,3 +65,32 @@ struct KpTables {
     uint32_t maxhs;                  // capacity of a tile's high-split list (7 per high position, rounded to 4)
     uint32_t warp_smem_bytes[2];     // per-warp shared memory of the DP kernel [wide]
 };
+
+// ---------------------------------------------------------------------------------------------------
+// Fiber kernel (kp_fiber.cuh): a FOURTH position on chip.  One high position of radix 15 (an N), the "fiber position",
+// joins the three low positions: a CTA owns the 15 tiles that differ only in that digit (a fiber, 15^4 = 50 625
+// patterns, 202.5 KB of float32 in shared memory), so the splits of the fiber position never leave the SM.  Inside
+// the CTA the 15 x 225 rows are processed level by level (level of the fiber digit + level of the row), and the rows
+// of a tile are kept in LEVEL order ("frow") in shared memory; the HBM layout (schedule order, "srow") is unchanged.
+// ---------------------------------------------------------------------------------------------------
+#define KP_FIBER_ROWS 225
+#define KP_FIBER_DIGITS 15
+#define KP_FIBER_ROW_LEVELS 7
+struct KpFiberTables {
+    int32_t ok;                // the general pattern has the all-N tile shape and an N among its high positions
+    int32_t fe;                // effective index of the fiber position
+    int32_t fhi;               // its index among the high positions
+    uint32_t hw;               // its tile weight
+    uint32_t nfibers;
+    uint32_t lvl_start[KP_FIBER_ROW_LEVELS + 1];   // rows of row-level l: frow in [lvl_start[l], lvl_start[l + 1])
+    // blob (device global; CTAs copy it to shared memory): byte offsets
+    uint32_t ft_bytes;
+    uint32_t ft_srow_of_frow;  // u8  [225]
+    uint32_t ft_frow_of_srow;  // u8  [232]  (padding rows -> 0xFF)
+    uint32_t ft_xs_off;        // u16 [226]  by frow; cross-row splits (CSR)
+    uint32_t ft_xs;            // u16 [...]  frow of c1 | frow of c2 << 8
+    uint32_t ft_bs_off;        // u16 [226]  by frow; base rows covered by the row (CSR)
+    uint32_t ft_bs;            // u8  [...]  base-row index
+    uint32_t maxhs;            // capacity of a fiber's high-split list
+};
+

@@ -194,6 +194,43 @@ class PartitionPlan:
             return train, kept
         return np.float32(top[0]), np.float32(top[1])
 
+    # -- CV jobs without a host round trip ------------------------------------------------------
+    CV_SLOTS = 3      # staging areas in rotation (a job's results are read two submissions later)
+
+    def cv_job_submit(self, eMtot, eUtot, eMte, eUte, max_count, alpha, beta, penalty, cap=65536):
+        """Queue one CV job (DP, backtrack, leaf losses, copies to pinned host memory) and return a ticket without
+        waiting.  The train tables rotate over two buffers and the staging areas over CV_SLOTS, so up to two jobs may be
+        outstanding: call cv_job_result on the oldest ticket before submitting a third."""
+        torch = _torch()
+        seq = getattr(self, "_cv_seq", 0)
+        self._cv_seq = seq + 1
+        train = self._buffer(f"cvtrain{seq % 2}", int(self.info.table_elems), torch.float32)
+        kept = self._buffer(f"cvkept{seq % 2}", int(self.info.kept_elems), torch.int16)
+        ws = self._buffer("btws", int(self.lib.kp_backtrack_ws_bytes(cap)), torch.uint8)
+        stages = self.__dict__.setdefault("_cv_stage", {})
+        key = (seq % self.CV_SLOTS, cap)
+        if key not in stages:
+            stages[key] = torch.empty(int(self.lib.kp_cv_stage_bytes(cap)), dtype=torch.uint8).pin_memory()
+        stage = stages[key]
+        check(self.lib.kp_cv_job_enqueue(self.handle, eMtot.data_ptr(), eUtot.data_ptr(), eMte.data_ptr(), eUte.data_ptr(),
+                                         int(max_count), float(alpha), float(beta), float(penalty), train.data_ptr(),
+                                         kept.data_ptr(), ws.data_ptr(), cap, stage.data_ptr(), self._stream()), "kp_cv_job_enqueue")
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return (ev, stage, cap, (eMtot, eUtot, eMte, eUte, max_count, alpha, beta, penalty))
+
+    def cv_job_result(self, ticket):
+        """(np.float32 train, np.float32 held-out) loss of the general pattern for a submitted job (waits for it)."""
+        ev, stage, cap, job = ticket
+        ev.synchronize()
+        top = (ctypes.c_float * 2)()
+        rc = self.lib.kp_cv_job_finish(stage.data_ptr(), cap, ctypes.cast(top, ctypes.c_void_p))
+        if rc == KP_ERR_CAPACITY:   # the partition has more leaves than the workspace held: run this job again, synchronously
+            return self.cv_job(*job, cap=cap * 8)
+        if rc != 0:
+            raise KpError("kp_cv_job_finish: " + self.lib.kp_last_error().decode())
+        return np.float32(top[0]), np.float32(top[1])
+
     def cv_heldout(self, root, cap=65536):
         """Held-out loss of the best partition of pattern `root` for the last cv_job (reference: test_score_mem[root])."""
         torch = _torch()
