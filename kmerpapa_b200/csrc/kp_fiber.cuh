@@ -383,11 +383,17 @@ __global__ void __launch_bounds__(KP_FIBER_THREADS, 1) kp_dp_fiber_kernel(const 
 #pragma unroll
                         for (int b = 0; b < NB; b++)
                             if ((bm >> b) & 1u) { M_ += m[b]; U_ += u[b]; }
-                        double s_, lp_, l1_;
-                        if (leafrow && d < NB) s_ = kp_leaf_score_nl(M_, U_, alpha, beta, penalty, logtab);
-                        else s_ = kp_self_score_t<C>(M_, U_, alpha, beta, penalty, logtab, K, lp_, l1_);
-                        const float sf = __double2float_rn(s_);
-                        if ((double)sf > s_) rupm |= 1u << d;
+                        float sf;
+                        bool ru;
+                        const bool leafcell = leafrow && d < NB;
+                        if (leafcell || !kp_self_score_fast<C>(M_, U_, alpha, beta, penalty, logtab, K, sf, ru)) {
+                            // k-mers (scipy's formula), and the one score in 10^5 the fast bound cannot decide: exact
+                            const double s_ = leafcell ? kp_leaf_score_nl(M_, U_, alpha, beta, penalty, logtab)
+                                                       : kp_self_score_exact_nl<C>(M_, U_, alpha, beta, penalty, logtab);
+                            sf = __double2float_rn(s_);
+                            ru = (double)sf > s_;
+                        }
+                        if (ru) rupm |= 1u << d;
 #pragma unroll
                         for (int c = 0; c < R0; c++)
                             if (c == d) sfx[c] = sf;

@@ -78,6 +78,101 @@ __device__ __forceinline__ double kp_self_score_t(C M, C U, double alpha, double
     return U > 0 ? s2 : s;
 }
 
+// out-of-line copy of the exact score: after kp_self_score_fast it is the rare path, and a call keeps its registers
+// (the glibc-exact log needs a dozen live doubles) out of the hot loop
+template <typename C>
+__device__ __noinline__ double kp_self_score_exact_nl(C M, C U, double alpha, double beta, double penalty, const double2 *tab)
+{
+    const KpLogK K = kp_logk_load();
+    double lp, l1;
+    return kp_self_score_t<C>(M, U, alpha, beta, penalty, tab, K, lp, l1);
+}
+
+// FAST self-score with a rigorous error bound.  What the DP needs from the float64 score s of the reference
+// (w_numba.py:56-64) is only  sf = RN_f32(s)  and the bit  (double)sf > s.  Both follow from ANY float64 approximation
+// s~ with |s~ - s| <= eps unless s~ lies within eps of a float32 rounding boundary or of sf itself, which happens for
+// about one score in 10^5; only those take the glibc-exact path.  s~ costs a third of the exact score: the quotient by
+// a reciprocal seed and two Newton steps instead of the IEEE division, log p by glibc's table and polynomial without the
+// hi/lo compensation, log(1-p) by a plain Horner evaluation of glibc's near-1 polynomial (five terms below 2^-8).
+// Error budget (pen >= 0, 2^-1000 < p < 2^-4, so q = 1 - p > 0.9375 and |ln p| > 2.7; a = pen + t1 + t2 with
+// t1 = -2 M ln p >= 0, t2 = -2 U ln q >= 0):
+//   quotient        |p~ - p| <= 1.2 * 2^-50 p                 -> 2M * 1.2 * 2^-50 <= 2^-51 t1;  via q: 2U * 1.3 * 2^-50 p <= 2^-49 t2
+//   rounding of q   |q~ - q| <= 2^-53 more, / q               -> 2U * 1.07 * 2^-53 <= 2^-51 (M + U)      [not relative to t2]
+//   logs            this approximation <= 2^-50 relative, glibc's own < 1 ulp of the true log     -> 2^-49 (t1 + t2)
+//   mul / add       four roundings in each sequence                                                -> 2^-50 a
+//   total           < 2^-48 a + 2^-51 (M + U);   the bound used is  eps = 2^-46 a + 2^-49 (M + U).
+// Returns false when the arguments are outside the window above (the caller then takes the exact path).
+template <typename C>
+__device__ __forceinline__ bool kp_self_score_fast(C M, C U, double alpha, double beta, double penalty, const double2 *tab,
+                                                   const KpLogK &K, float &sf, bool &rup)
+{
+    const double Md = kp_cnt2d(M), Ud = kp_cnt2d(U), Sd = kp_cnt2d((C)(M + U));
+    const double num = KP_ADD(Md, alpha), den = KP_ADD(KP_ADD(Sd, alpha), beta);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    double e = KP_FMA(-den, r, 1.0);
+    r = KP_FMA(r, e, r);
+    e = KP_FMA(-den, r, 1.0);
+    r = KP_FMA(r, e, r);
+    const double p = KP_MUL(num, r);
+    const int phi = __double2hiint(p), dhi = __double2hiint(den);
+    // 2^-1000 <= p < 2^-4, 2^-500 <= den < 2^500 (the reciprocal seed flushes subnormals), pen >= 0
+    bool ok = (unsigned)(phi - 0x01700000) < (unsigned)(0x3fb00000 - 0x01700000) &&
+              (unsigned)(dhi - 0x20b00000) < (unsigned)(0x5f300000 - 0x20b00000) && penalty >= 0.0;
+    // log p~
+    const double *A = kpc_logA;
+    const unsigned thi = (unsigned)phi - 0x3fe60000u;
+    const int i = (int)((thi >> 13) & 127u);
+    const int k = (int)thi >> 20;
+    const double z = __hiloint2double(phi - (int)(thi & 0xfff00000u), __double2loint(p));
+    const double2 t = tab[i];
+    const double kd = (double)k;
+    const double rr = KP_FMA(z, t.x, -1.0);
+    const double r2 = KP_MUL(rr, rr);
+    const double w = KP_FMA(kd, KP_LOG_LN2HI, t.y);
+    double q1 = KP_FMA(rr, A[4], K.a3);
+    const double q5 = KP_FMA(rr, A[2], K.a1);
+    q1 = KP_FMA(q1, r2, q5);
+    double lo = KP_FMA(kd, KP_LOG_LN2LO, rr);
+    lo = KP_FMA(r2, A[0], lo);
+    lo = KP_FMA(KP_MUL(rr, r2), q1, lo);
+    const double logp = KP_ADD(w, lo);
+    // log q~, q~ = 1 - p~ in (0.9375, 1]: ln(1 + x) = x + x^2 (B0 + x (B1 + ...)), x = q~ - 1 exactly
+    const double *B = kpc_logB;
+    const double x = KP_SUB(KP_SUB(1.0, p), 1.0);
+    const double x2 = KP_MUL(x, x);
+    double y;
+    if (phi < 0x3f700000) {   // p < 2^-8: the terms beyond x^6 are below 2^-50 |x|
+        y = KP_FMA(x, B[4], B[3]);
+        y = KP_FMA(y, x, B[2]);
+        y = KP_FMA(y, x, K.b1);
+        y = KP_FMA(y, x, -0.5);
+    } else {
+        y = KP_FMA(x, B[10], B[9]);
+        y = KP_FMA(y, x, B[8]);
+        y = KP_FMA(y, x, K.b7);
+        y = KP_FMA(y, x, B[6]);
+        y = KP_FMA(y, x, B[5]);
+        y = KP_FMA(y, x, K.b4);
+        y = KP_FMA(y, x, B[3]);
+        y = KP_FMA(y, x, B[2]);
+        y = KP_FMA(y, x, K.b1);
+        y = KP_FMA(y, x, -0.5);
+    }
+    const double logq = KP_FMA(x2, y, x);
+    const double t1 = KP_MUL(KP_MUL(-2.0, Md), logp), t2 = KP_MUL(KP_MUL(-2.0, Ud), logq);
+    double sa = M > 0 ? KP_ADD(penalty, t1) : penalty;
+    sa = U > 0 ? KP_ADD(sa, t2) : sa;
+    const double eps = KP_FMA(sa, 0x1p-46, KP_MUL(Sd, 0x1p-49));   // pen >= 0: sa = pen + t1 + t2 = a
+    const double slo = KP_SUB(sa, eps), shi = KP_ADD(sa, eps);
+    const float flo = __double2float_rn(slo), fhi = __double2float_rn(shi);
+    const double fd = (double)flo;
+    sf = flo;
+    rup = fd > shi;
+    ok = ok && flo == fhi && (fd > shi || fd < slo) && sa < 0x1p120;   // NaN / inf / ambiguous: exact path
+    return ok;
+}
+
 // held-out -2 log-lik of a pattern kept whole (_CV.py:73-78), branch-free
 template <typename C>
 __device__ __forceinline__ double kp_test_ll_t(C Mt, C Ut, double logp, double log1mp)
@@ -575,11 +670,17 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
 #pragma unroll
                         for (int b = 0; b < NB; b++)
                             if ((bm >> b) & 1u) { M_ += m[b]; U_ += u[b]; }
-                        double s_, lp_, l1_;
-                        if (leafrow && d < NB) s_ = kp_leaf_score_nl(M_, U_, alpha, beta, penalty, logtab);
-                        else s_ = kp_self_score_t<C>(M_, U_, alpha, beta, penalty, logtab, K, lp_, l1_);
-                        const float sf = __double2float_rn(s_);
-                        if ((double)sf > s_) rupm |= 1u << d;
+                        float sf;
+                        bool ru;
+                        const bool leafcell = leafrow && d < NB;
+                        if (leafcell || !kp_self_score_fast<C>(M_, U_, alpha, beta, penalty, logtab, K, sf, ru)) {
+                            // k-mers (scipy's formula), and the one score in 10^5 the fast bound cannot decide: exact
+                            const double s_ = leafcell ? kp_leaf_score_nl(M_, U_, alpha, beta, penalty, logtab)
+                                                       : kp_self_score_exact_nl<C>(M_, U_, alpha, beta, penalty, logtab);
+                            sf = __double2float_rn(s_);
+                            ru = (double)sf > s_;
+                        }
+                        if (ru) rupm |= 1u << d;
 #pragma unroll
                         for (int c = 0; c < R0; c++)
                             if (c == d) sfx[c] = sf;

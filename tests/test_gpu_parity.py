@@ -176,8 +176,9 @@ def test_random_against_oracle(eng, oracle, gen_pat, seed):
     assert np.array_equal(patnums, oracle.backtrack(gen_pat, ref["split"]))
 
 
-@pytest.mark.parametrize("regime", ["rate_near_one", "half", "tiny_counts", "huge_counts", "zeros", "penalty_ties"])
-@pytest.mark.parametrize("gen_pat", ["NNNNN", "NNMNNN"])
+@pytest.mark.parametrize("regime", ["rate_near_one", "half", "tiny_counts", "huge_counts", "zeros", "penalty_ties", "low_rates",
+                                    "kept_whole"])
+@pytest.mark.parametrize("gen_pat", ["NNNNN", "NNMNNN", "NNNNNN"])
 def test_count_regimes_against_oracle(eng, oracle, gen_pat, regime):
     """Regimes that stress the score filter (a float32 bound decides whether the exact FP64 score is computed): rates
     near 1 (absolute error of the fast log), rates around 1/2, counts of a few units, counts near 2^31, mostly empty
@@ -196,17 +197,25 @@ def test_count_regimes_against_oracle(eng, oracle, gen_pat, regime):
         U = rng.integers(0, 4, size=nk)
         M = rng.integers(0, 3, size=nk)
     elif regime == "huge_counts":
-        U = rng.integers(10 ** 6, (2 ** 31 - 10 ** 6) // nk, size=nk)
+        hi = (2 ** 31 - 10 ** 6) // nk
+        U = rng.integers(min(10 ** 6, hi // 2), hi, size=nk)
         M = rng.binomial(U, 0.001)
     elif regime == "zeros":
         keep = rng.random(nk) < 0.02
         U = rng.integers(1, 5000, size=nk) * keep
         M = rng.binomial(U, 0.05)
+    elif regime == "low_rates":     # the fast score path (kp_self_score_fast): rates on both sides of its 2^-8 switch, up to 2^-4
+        U = rng.integers(10 ** 4, 10 ** 6, size=nk)
+        M = rng.binomial(U, np.exp(rng.uniform(np.log(1e-6), np.log(0.07), size=nk)))
+    elif regime == "kept_whole":    # a penalty so large that every pattern is kept whole: every stored value is a self-score
+        U = 1 + rng.negative_binomial(2, 2 / (2 + 33000.0), size=nk)
+        M = rng.binomial(U, np.minimum(0.5, 1e-3 * np.exp(rng.normal(0, 0.7, size=nk))))
     else:
         U = np.full(nk, 1000)
         M = np.full(nk, 10)
     U[0], M[0] = max(U[0], 5), max(M[0], 1)
-    for alpha, pen in ((1.0, 4.0), (0.5, 0.0)) if regime != "penalty_ties" else ((1.0, 0.0), (1.0, 2.0)):
+    grid = {"penalty_ties": ((1.0, 0.0), (1.0, 2.0)), "kept_whole": ((1.0, 1e6), (0.01, 3e3))}.get(regime, ((1.0, 4.0), (0.5, 0.0)))
+    for alpha, pen in grid:
         mu = M.sum() / (M.sum() + U.sum())
         beta = alpha * (1 - mu) / mu
         _, best, split, patnums = _run_single(eng, gen_pat, M, U, alpha, beta, pen)
