@@ -17,7 +17,7 @@ from math import log
 import numpy as np
 
 from . import __version__, iupac
-from .io_utils import downsize_contextD, read_input
+from .io_utils import downsize_contextD_device as downsize_contextD, read_input
 from .score_utils import beta_from_totals, get_loss
 
 

@@ -833,6 +833,7 @@ int kp_shard_create(kp_plan *p, int rank, int world, int replicate, kp_shard **o
     s->view.hw_top = s->hw_top;
     const uint64_t own_tiles = (uint64_t)s->nslots * s->hw_top;
     s->local_tiles = own_tiles;
+    std::vector<uint8_t> cell_owner;   // two-dimensional ownership: owner of every (top digit, second digit) cell
     if (s->replicate) {   // full-size table, global tile numbers; readers of a digit = owners of its strict supersets
         s->local_tiles = t.ntiles;
         for (int d = 0; d < (int)s->radix_top; d++) {
@@ -844,6 +845,50 @@ int kp_shard_create(kp_plan *p, int rank, int world, int replicate, kp_shard **o
             }
             s->view.push_mask[d] = (uint8_t)mask;
         }
+        if (t.nhigh >= 2 && world > 1 && !getenv("KP_SHARD_1D")) {
+            // Two-dimensional ownership over the two top high positions: cell (d_top, d_second) belongs to rank
+            // (i_top + i_second) mod world, i = index of the digit in order of decreasing level.  Every wave (= level)
+            // is spread over all ranks, and so is the traffic: a tile is pushed to the owners of its parents along BOTH
+            // positions (about four peers at eight ranks), but no rank receives more than its share.
+            const int e2 = t.highpos[t.nhigh - 2];
+            const int r1 = t.radix[e], r2 = t.radix[e2];
+            auto level_index = [&](int pos, std::vector<int> &idx) {
+                const int radix = t.radix[pos];
+                std::vector<int> digits(radix);
+                for (int d = 0; d < radix; d++) digits[d] = d;
+                auto lvl = [&](int d) { unsigned m = t.digit_mask[pos][d]; return (int)((m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + ((m >> 3) & 1)); };
+                std::stable_sort(digits.begin(), digits.end(), [&](int a, int b) { return lvl(a) > lvl(b); });
+                idx.assign(radix, 0);
+                for (int i = 0; i < radix; i++) idx[digits[i]] = i;
+            };
+            std::vector<int> i1, i2;
+            level_index(e, i1);
+            level_index(e2, i2);
+            s->view.two_d = 1;
+            s->view.hw_second = t.highw[e2];
+            cell_owner.assign((size_t)r1 * r2, 0);
+            for (int d1 = 0; d1 < r1; d1++)
+                for (int d2 = 0; d2 < r2; d2++) cell_owner[(size_t)d2 + (size_t)r2 * d1] = (uint8_t)((i1[d1] + i2[d2]) % world);
+            for (int d1 = 0; d1 < r1; d1++)
+                for (int d2 = 0; d2 < r2; d2++) {
+                    const size_t c = (size_t)d2 + (size_t)r2 * d1;
+                    unsigned mask = 0;
+                    for (int q = 0; q < r1; q++) {
+                        const unsigned md = t.digit_mask[e][d1], mq = t.digit_mask[e][q];
+                        if (q != d1 && (md & mq) == md) mask |= 1u << cell_owner[(size_t)d2 + (size_t)r2 * q];
+                    }
+                    for (int q = 0; q < r2; q++) {
+                        const unsigned md = t.digit_mask[e2][d2], mq = t.digit_mask[e2][q];
+                        if (q != d2 && (md & mq) == md) mask |= 1u << cell_owner[(size_t)q + (size_t)r2 * d1];
+                    }
+                    mask &= ~(1u << cell_owner[c]);
+                    s->view.owner2[c] = cell_owner[c];
+                    s->view.push_mask2[c] = (uint8_t)mask;
+                }
+            uint32_t cells = 0;
+            for (uint8_t o : cell_owner) cells += o == rank;
+            s->nslots = cells;   // reported as top_digits: the number of (top, second) cells this rank owns
+        }
     }
     if (s->local_tiles >= (1ull << 28)) { delete s; return fail("kp_shard_create: more than 2^28 tiles per rank"); }
     // this rank's tiles of every wave, in the order of the plan's tile list
@@ -853,11 +898,12 @@ int kp_shard_create(kp_plan *p, int rank, int world, int replicate, kp_shard **o
     for (size_t l = 0; l < nhl; l++) {
         for (uint64_t i = p->host.hl_off[l]; i < p->host.hl_off[l + 1]; i++) {
             const uint32_t tile = p->host.tile_order[i];
-            if (s->view.owner[tile / s->hw_top] == rank) mine.push_back(tile);
+            const int own = s->view.two_d ? cell_owner[tile / s->view.hw_second] : s->view.owner[tile / s->hw_top];
+            if (own == rank) mine.push_back(tile);
         }
         s->hl_off[l + 1] = mine.size();
     }
-    if (mine.size() != own_tiles) { delete s; return fail("kp_shard_create: internal: tile count"); }
+    if (!s->view.two_d && mine.size() != own_tiles) { delete s; return fail("kp_shard_create: internal: tile count"); }
     cudaError_t e1 = cudaMalloc(&s->d_best, (size_t)s->local_tiles * t.tile_stride * sizeof(float));
     cudaError_t e2 = cudaMalloc(&s->d_kept, (size_t)s->local_tiles * t.rp * sizeof(uint16_t));
     cudaError_t e3 = cudaMalloc(&s->d_tiles, sizeof(uint32_t) * (mine.size() + 1));

@@ -280,10 +280,22 @@ struct KpView {
     uint32_t hw_top;
     uint8_t owner[16], slot[16];
     uint8_t push_mask[16];   // replicated mode: ranks (bit r) that own a strict superset of the digit, i.e. read its tiles
+    // replicated mode, two-dimensional ownership (general patterns with at least two high positions): the owner of a tile
+    // depends on the digits of the TWO top high positions, cell = tile / hw_second = d_second + radix_second * d_top.
+    // Spreads the inbound NVLink traffic, which with one-dimensional ownership piles up on the owner of digit N.
+    uint32_t hw_second;
+    uint32_t two_d;
+    uint8_t owner2[256];     // cell -> owner rank
+    uint8_t push_mask2[256]; // cell -> ranks that own a parent of the cell's tiles along either of the two positions
 };
 
 __device__ __forceinline__ void kp_view_tile(const KpView &v, unsigned long long tile, int &rank, unsigned long long &ltile)
 {
+    if (v.two_d) {   // replicated tables hold global tile numbers
+        rank = v.owner2[tile / v.hw_second];
+        ltile = tile;
+        return;
+    }
     const unsigned long long d = tile / v.hw_top;
     rank = v.owner[d];
     ltile = (unsigned long long)v.slot[d] * v.hw_top + (tile - d * v.hw_top);
@@ -454,7 +466,7 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
         const int nhs = *s_nhs;
         float4 *otile = (float4 *)(p.best + (size_t)ltile * stride);
         uint32_t pushm = 0;   // replicated mode: peers that will read this tile
-        if (SHARD == 2) pushm = p.view.push_mask[tile / p.view.hw_top];
+        if (SHARD == 2) pushm = p.view.two_d ? p.view.push_mask2[tile / p.view.hw_second] : p.view.push_mask[tile / p.view.hw_top];
 
         // ---- phase D: stream the child tiles of the high-position splits for ALL rows of the tile; the running
         //      minimum of row r is parked in S[r] until the row's turn in the schedule.  One flattened software

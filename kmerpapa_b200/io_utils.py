@@ -129,3 +129,37 @@ def downsize_contextD(table, general_pattern, length):
         for i, c in enumerate(counts):
             acc[i] += c
     return out, general_pattern[window[0]:window[1]]
+
+
+def downsize_contextD_device(table, general_pattern, length):
+    """downsize_contextD with the sums formed on the GPU.  Collapsing a k-mer to its centred
+    `length`-mer is a shift of its packed 4-bit code, and summing the counts of equal short k-mers is what the packing
+    kernel K1 (kp_pack_counts: atomic adds into the dense k-mer table) already does for duplicate input lines, so the
+    short table is K1 on the shifted codes.  Same return value as downsize_contextD, keys in the same (first seen) order."""
+    import numpy as np
+
+    from . import iupac
+    from .engine import get_plan
+
+    kmers = list(table.keys())
+    vals = list(table.values())
+    if not kmers or any(len(v) != 2 for v in vals) or len(kmers[0]) > 16:
+        return downsize_contextD(table, general_pattern, length)
+    assert length is not None
+    assert len(kmers[0]) > length, f"k-mer:{kmers[0]} cannot be reduced to length {length}"
+    lo, hi = _centre_window(len(kmers[0]), length)
+    short_gen = general_pattern[lo:hi]
+    codes = (iupac.kmer_codes(kmers) >> np.uint64(4 * lo)) & np.uint64((1 << (4 * length)) - 1)
+    pos = np.array([v[0] for v in vals], dtype=np.int64)
+    neg = np.array([v[1] for v in vals], dtype=np.int64)
+    plan = get_plan(short_gen, lite=True)
+    kM, kU = plan.pack_counts(codes, pos, neg, name="downsize_k")
+    M, U = kM[: plan.nkmer].cpu().numpy(), kU[: plan.nkmer].cpu().numpy()
+    index = {km: i for i, km in enumerate(iupac.matches(short_gen))}
+    out = {}
+    for kmer in kmers:
+        short = kmer[lo:hi]
+        if short not in out:
+            i = index[short]
+            out[short] = [int(M[i]), int(U[i])]
+    return out, short_gen
