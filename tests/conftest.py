@@ -26,3 +26,20 @@ def oracle():
 
     kp_oracle.build()
     return kp_oracle
+
+
+def free_gpu_memory():
+    """Drop every cached plan and hand torch's cached blocks back to the driver: the tests that launch torchrun children
+    on the same GPUs need the memory this process has accumulated (full-size tables are tens of GB)."""
+    import gc
+
+    import torch
+
+    from kmerpapa_b200 import engine
+
+    engine.clear_plans()
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+

@@ -63,6 +63,9 @@ def test_cli_sharded_over_gpus():
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs at least two GPUs")
+    from conftest import free_gpu_memory
+
+    free_gpu_memory()
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}",
                         "--master-addr", "127.0.0.1", "--master-port", "29612", os.path.join(here, "mgpu_cli_check.py")],

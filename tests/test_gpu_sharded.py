@@ -94,6 +94,9 @@ def test_sharded_multiprocess():
     if n < 2:
         pytest.skip("needs at least two GPUs")
     world = 2 if n < 4 else 4
+    from conftest import free_gpu_memory
+
+    free_gpu_memory()
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(here, "mgpu_sharded_check.py"),
@@ -109,10 +112,13 @@ def test_cli_on_a_table_larger_than_one_gpu():
 
     if torch.cuda.device_count() < 2 or torch.cuda.get_device_properties(0).total_memory < 120e9:
         pytest.skip("needs two GPUs with at least 120 GB each")
+    from conftest import free_gpu_memory
+
+    free_gpu_memory()   # the children need (almost) all of both GPUs
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
                         "127.0.0.1", "--master-port", "29613", os.path.join(root, "tools", "cli_n9_demo.py")],
                        capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-6000:]
     assert "rc=0" in r.stdout and "General pattern: NNNNNNNNN" in r.stdout and "loss=" in r.stdout
 
