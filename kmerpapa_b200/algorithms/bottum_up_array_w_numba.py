@@ -67,8 +67,8 @@ def _cached_free(device):
 
 
 def _sharded_partition(plan, eM, eU, max_count, alpha, beta, penalty, rank, world):
-    """One DP over all ranks of the process group (kmerpapa_b200/sharded.py).  Returns None when this general pattern
-    cannot be sharded over `world` ranks (every rank takes the same decision: it depends on the plan only)."""
+    """One DP over all ranks of the process group (kmerpapa_b200/sharded.py).  Returns None when the DP fits every rank's
+    GPU or this general pattern cannot be sharded over `world` ranks (the ranks agree on both through an all_reduce)."""
     import torch
 
     from .. import sharded
@@ -76,7 +76,10 @@ def _sharded_partition(plan, eM, eU, max_count, alpha, beta, penalty, rank, worl
 
     import torch.distributed as dist
 
-    if fits_one_gpu(plan):
+    # One decision for all ranks (free memory may differ from GPU to GPU): shard as soon as ONE rank cannot hold the DP.
+    fits = torch.tensor([1 if fits_one_gpu(plan) else 0], dtype=torch.int32, device=plan.device)
+    dist.all_reduce(fits, op=dist.ReduceOp.MIN)
+    if int(fits.item()) == 1:
         # the table fits one GPU: mapping the peers' shards (CUDA IPC, 0.1-0.3 s) costs more than the one DP gains
         # (tools/shard_overhead.py); callers that run many DPs keep a ShardedDP(replicate=True) themselves
         return None
