@@ -40,6 +40,10 @@ int fail_capacity(const std::string &msg)
 
 }  // namespace
 
+#ifndef KP_EVICT_TOP
+#define KP_EVICT_TOP 0   // top high positions whose child tiles are loaded with an L2 evict-first policy (KP_EVICT_TOP in the environment)
+#endif
+
 struct kp_plan {
     KpHostPlan host;
     int device = 0;
@@ -67,6 +71,7 @@ struct kp_plan {
     int fiber_dbg = 0;               // KP_FIBER_DBG: timing experiments (results are wrong when set)
     bool use_fiber = false;          // KP_DP_KERNEL=fiber|rows: which kernel family runs the unsharded DP
     int pf_dist = KP_PF_DIST;        // KP_PF_DIST: L2 prefetch distance of the child-tile stream
+    int evict_top = KP_EVICT_TOP;    // KP_EVICT_TOP: top high positions whose child tiles are loaded L2-evict-first
     bool one_launch = false;         // KP_ONE_LAUNCH=1: all waves in one launch
 };
 
@@ -207,6 +212,7 @@ static int plan_create(const char *gen_pat, int device, bool lattice, kp_plan **
     }
     p->coop_launch = prop.cooperativeLaunch != 0 && !getenv("KP_NO_COOP_BACKTRACK");
     if (const char *e = getenv("KP_PF_DIST")) p->pf_dist = atoi(e);
+    if (const char *e = getenv("KP_EVICT_TOP")) p->evict_top = atoi(e);
     if (const char *e = getenv("KP_ONE_LAUNCH")) p->one_launch = e[0] == '1';
     for (int wide = 0; wide < 2; wide++) {
         size_t fixed = 2048 + t.rt_bytes, per_warp = t.warp_smem_bytes[wide];
@@ -485,6 +491,7 @@ static int dp_counts(kp_plan *p, const int64_t *d_expM, const int64_t *d_expU, c
     prm.best = d_best;
     prm.flags = d_kept;
     prm.pf_dist = p->pf_dist;
+    prm.evict_top = p->evict_top < p->host.t.nhigh ? p->evict_top : 0;
     return launch_dp(p, wide, prm, (cudaStream_t)stream);
 }
 

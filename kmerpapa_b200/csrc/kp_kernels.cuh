@@ -266,6 +266,17 @@ __device__ __forceinline__ float2 kp_score_lower_bound2(float2 Mf, float2 Uf, fl
     return __fadd2_rn(est, make_float2(-mar.x, -mar.y));
 }
 
+// 16-byte read-only load with an L2 cache policy (createpolicy): used for child tiles nobody re-reads while they could
+// still be in L2 (children along the top tile position: their other parents are thousands of tiles away in the claim
+// order), so that they do not push out the lines sibling tiles are about to share
+__device__ __forceinline__ float4 kp_ldg_policy(const float4 *ptr, unsigned long long policy)
+{
+    float4 v;
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(policy));
+    return v;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K3+K4: lazily fused self-score + min-plus recurrence
 // ---------------------------------------------------------------------------------------------------
@@ -309,6 +320,7 @@ struct KpDpParams {
     uint32_t *counter;          // next unclaimed entry of tile_list (zeroed before the launch)
     int leaf_wave;              // wave 0: rows of level 0 hold k-mers at the single-nucleotide digits
     int pf_dist;                // L2 prefetch distance of the child-tile stream, in (32 rows x 1 split) steps
+    int evict_top;              // child tiles along the top `evict_top` high positions are loaded with an L2 evict-first policy
     const long long *e0, *e1;   // expanded counts M, U  [ntiles][tile_kmers]
     const long long *s0, *s1;   // CV job: held-out expanded counts, subtracted on the fly (train = total - held-out); else null
     double alpha, beta, penalty;
@@ -377,6 +389,8 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
     const float alpha_f = (float)alpha, ab_f = (float)(alpha + beta), penalty_f = (float)penalty;
     const float INF = __int_as_float(0x7f800000);
     const float *tbase = p.best;
+    unsigned long long pol_first;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
 
     // Tiles are claimed in list order (ascending tile number): the tiles in flight on the whole GPU are then
     // always neighbours in the pattern lattice, which share child tiles, so those re-reads hit in L2.
@@ -428,6 +442,11 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
                 }
             }
             if (lane == 0) *s_nhs = total;
+            if (!SHARDED && !ONE_LAUNCH) {   // first split of the top `evict_top` positions (the list is in position order)
+                const int first = nhigh - p.evict_top;
+                const int ptop_ = p.evict_top > 0 ? __shfl_sync(0xffffffffu, off, first > 0 ? first : 0) : 0x7fffffff;
+                if (lane == 0) s_nhs[1] = ptop_;
+            }
         }
         if (ONE_LAUNCH && wave > 0) {
             // ---- wait for the child tiles.  They sit at most three waves back (a split lowers one position by at
@@ -464,6 +483,7 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
         }
         __syncwarp();
         const int nhs = *s_nhs;
+        const int ptop = (!SHARDED && !ONE_LAUNCH) ? s_nhs[1] : 0x7fffffff;
         float4 *otile = (float4 *)(p.best + (size_t)ltile * stride);
         uint32_t pushm = 0;   // replicated mode: peers that will read this tile
         if (SHARD == 2) pushm = p.view.two_d ? p.view.push_mask2[tile / p.view.hw_second] : p.view.push_mask[tile / p.view.hw_top];
@@ -494,7 +514,7 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
             const uint32_t *pf_hs = (lane & 16) ? hs2 : hs1;
             const int pf_g = (lane >> 2) & 3, pf_line = (lane & 3) * 8;
             const float4 *pf_ptr = tb4 + pf_g * rp + pf_line;
-            const bool pf_on = pf_g < NG;
+            const bool pf_on = pf_g < NG && p.pf_dist >= 0;   // KP_PF_DIST < 0: no L2 prefetch at all
 #define KP_FL_PREFETCH()                                                                              \
     if (pchunk < nrows) {                                                                             \
         const uint32_t ph_ = pf_hs[ps];                                                               \
@@ -514,9 +534,16 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
             a_ = (const float4 *)p.view.best[h1_ >> 28] + lrowc + (size_t)(h1_ & 0x0fffffffu) * stride4; \
             b_ = (const float4 *)p.view.best[h2_ >> 28] + lrowc + (size_t)(h2_ & 0x0fffffffu) * stride4; \
         }                                                                                             \
-        _Pragma("unroll") for (int g = 0; g < NG; g++) {   /* single launch: the table is written by this kernel, no .nc */ \
-            xa[g] = ONE_LAUNCH ? __ldcg(a_ + g * rp) : __ldg(a_ + g * rp);                            \
-            xb[g] = ONE_LAUNCH ? __ldcg(b_ + g * rp) : __ldg(b_ + g * rp);                            \
+        if (!SHARDED && !ONE_LAUNCH && ls >= ptop) {   /* warp-uniform: no sibling will find these lines in L2 */ \
+            _Pragma("unroll") for (int g = 0; g < NG; g++) {                                          \
+                xa[g] = kp_ldg_policy(a_ + g * rp, pol_first);                                        \
+                xb[g] = kp_ldg_policy(b_ + g * rp, pol_first);                                        \
+            }                                                                                         \
+        } else {                                                                                      \
+            _Pragma("unroll") for (int g = 0; g < NG; g++) {   /* single launch: the table is written by this kernel, no .nc */ \
+                xa[g] = ONE_LAUNCH ? __ldcg(a_ + g * rp) : __ldg(a_ + g * rp);                        \
+                xb[g] = ONE_LAUNCH ? __ldcg(b_ + g * rp) : __ldg(b_ + g * rp);                        \
+            }                                                                                         \
         }                                                                                             \
         if (++ls == nhs) {                                                                            \
             ls = 0; lrow += 32;                                                                       \
