@@ -1,5 +1,6 @@
 // kp_api.cu — C ABI of libkpapa.so (see include/kmerpapa_b200.h for the contract).
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -40,6 +41,9 @@ int fail_capacity(const std::string &msg)
 
 }  // namespace
 
+#ifndef KP_PF_TOP
+#define KP_PF_TOP 0      // prefetch the splits of the top KP_PF_TOP high positions only (0: all)
+#endif
 #ifndef KP_EVICT_TOP
 #define KP_EVICT_TOP 0   // top high positions whose child tiles are loaded with an L2 evict-first policy (KP_EVICT_TOP in the environment)
 #endif
@@ -72,6 +76,7 @@ struct kp_plan {
     bool use_fiber = false;          // KP_DP_KERNEL=fiber|rows: which kernel family runs the unsharded DP
     int pf_dist = KP_PF_DIST;        // KP_PF_DIST: L2 prefetch distance of the child-tile stream
     int evict_top = KP_EVICT_TOP;    // KP_EVICT_TOP: top high positions whose child tiles are loaded L2-evict-first
+    int pf_top = KP_PF_TOP;          // KP_PF_TOP: only the splits of this many top high positions are prefetched (0: all)
     bool one_launch = false;         // KP_ONE_LAUNCH=1: all waves in one launch
 };
 
@@ -213,6 +218,7 @@ static int plan_create(const char *gen_pat, int device, bool lattice, kp_plan **
     p->coop_launch = prop.cooperativeLaunch != 0 && !getenv("KP_NO_COOP_BACKTRACK");
     if (const char *e = getenv("KP_PF_DIST")) p->pf_dist = atoi(e);
     if (const char *e = getenv("KP_EVICT_TOP")) p->evict_top = atoi(e);
+    if (const char *e = getenv("KP_PF_TOP")) p->pf_top = atoi(e);
     if (const char *e = getenv("KP_ONE_LAUNCH")) p->one_launch = e[0] == '1';
     for (int wide = 0; wide < 2; wide++) {
         size_t fixed = 2048 + t.rt_bytes, per_warp = t.warp_smem_bytes[wide];
@@ -492,6 +498,7 @@ static int dp_counts(kp_plan *p, const int64_t *d_expM, const int64_t *d_expU, c
     prm.flags = d_kept;
     prm.pf_dist = p->pf_dist;
     prm.evict_top = p->evict_top < p->host.t.nhigh ? p->evict_top : 0;
+    prm.pf_top = p->pf_top;
     return launch_dp(p, wide, prm, (cudaStream_t)stream);
 }
 
@@ -791,6 +798,105 @@ struct kp_shard {
     uint32_t *d_counters = nullptr;
 };
 
+
+// Two-dimensional shard ownership, improved by a deterministic local search (every rank runs it and gets the same table).
+// A tile must be pushed to every rank that owns one of its parents along either of the two top positions, and the DP is
+// NVLink-bound, so the search minimises the largest inbound (and outbound) cell count of any rank
+// while keeping every wave evenly spread: cells of the same level hold the same number of tiles in every wave.
+// Start: owner = (i_top + i_second) mod world.  At eight ranks the busiest rank's inbound volume falls from 128 to about
+// 70 of the 225 cells (one-dimensional ownership: 195).
+static void optimise_cell_owners(const KpTables &t, int e1, int e2, int world, std::vector<uint8_t> &owner)
+{
+    const int r1 = t.radix[e1], r2 = t.radix[e2], ncell = r1 * r2;
+    auto pc = [](unsigned m) { return (int)((m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + ((m >> 3) & 1)); };
+    std::vector<std::vector<int>> sup1(r1), sup2(r2);
+    for (int d = 0; d < r1; d++)
+        for (int q = 0; q < r1; q++)
+            if (q != d && (t.digit_mask[e1][d] & t.digit_mask[e1][q]) == t.digit_mask[e1][d]) sup1[d].push_back(q);
+    for (int d = 0; d < r2; d++)
+        for (int q = 0; q < r2; q++)
+            if (q != d && (t.digit_mask[e2][d] & t.digit_mask[e2][q]) == t.digit_mask[e2][d]) sup2[d].push_back(q);
+    std::vector<int> lvl(ncell);
+    int nlvl = 0;
+    for (int d1 = 0; d1 < r1; d1++)
+        for (int d2 = 0; d2 < r2; d2++) {
+            lvl[d2 + r2 * d1] = pc(t.digit_mask[e1][d1]) + pc(t.digit_mask[e2][d2]) - 2;
+            nlvl = std::max(nlvl, lvl[d2 + r2 * d1] + 1);
+        }
+    std::vector<int> inb(world), outb(world), wl((size_t)nlvl * world);
+    auto cost = [&]() {
+        std::fill(inb.begin(), inb.end(), 0);
+        std::fill(outb.begin(), outb.end(), 0);
+        std::fill(wl.begin(), wl.end(), 0);
+        for (int d1 = 0; d1 < r1; d1++)
+            for (int d2 = 0; d2 < r2; d2++) {
+                const int c = d2 + r2 * d1, o = owner[c];
+                wl[(size_t)lvl[c] * world + o]++;
+                unsigned dest = 0;
+                for (int q : sup1[d1]) dest |= 1u << owner[d2 + r2 * q];
+                for (int q : sup2[d2]) dest |= 1u << owner[q + r2 * d1];
+                dest &= ~(1u << o);
+                for (int r = 0; r < world; r++)
+                    if ((dest >> r) & 1u) { inb[r]++; outb[o]++; }
+            }
+        double imb = 0;
+        std::vector<int> own(world, 0);
+        for (int l = 0; l < nlvl; l++) {
+            int mx = 0, sum = 0;
+            for (int r = 0; r < world; r++) {
+                mx = std::max(mx, wl[(size_t)l * world + r]);
+                sum += wl[(size_t)l * world + r];
+                own[r] += wl[(size_t)l * world + r];
+            }
+            imb += mx - (double)sum / world;
+        }
+        imb += *std::max_element(own.begin(), own.end()) - (double)ncell / world;   // and the whole table evenly, too
+        return *std::max_element(inb.begin(), inb.end()) + 0.5 * *std::max_element(outb.begin(), outb.end()) + 3.0 * imb;
+    };
+    unsigned long long rng = 0x9E3779B97F4A7C15ull;
+    auto next = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (unsigned)(rng >> 33); };
+    double cur = cost(), best = cur, T = 3.0;
+    std::vector<uint8_t> best_owner = owner;
+    const int iters = 40000;
+    for (int it = 0; it < iters; it++) {
+        const int a = (int)(next() % (unsigned)ncell);
+        double c;
+        int b = -1;
+        uint8_t olda = owner[a];
+        if (next() & 1u) {
+            const uint8_t nw = (uint8_t)(next() % (unsigned)world);
+            if (nw == olda) continue;
+            owner[a] = nw;
+        } else {
+            b = (int)(next() % (unsigned)ncell);
+            if (owner[b] == olda) continue;
+            std::swap(owner[a], owner[b]);
+        }
+        c = cost();
+        // accept improvements always, deteriorations with probability 2^(-(c - cur) / T) (integer-only randomness: deterministic)
+        bool accept = c <= cur;
+        if (!accept) {
+            const double x = (c - cur) / T;
+            accept = x < 30.0 && (double)(next() & 0xFFFFFF) / 16777216.0 < exp2(-x);
+        }
+        if (accept) {
+            cur = c;
+            if (cur < best) { best = cur; best_owner = owner; }
+        } else if (b >= 0) {
+            std::swap(owner[a], owner[b]);
+        } else {
+            owner[a] = olda;
+        }
+        T = std::max(0.05, T * 0.9997);
+    }
+    owner = best_owner;
+    if (getenv("KP_SHARD_VERBOSE")) {
+        cost();
+        fprintf(stderr, "kp_shard: %d x %d cells over %d ranks: busiest rank receives %d cells, sends %d; cost %.2f -> %.2f\n", r1, r2, world,
+                *std::max_element(inb.begin(), inb.end()), *std::max_element(outb.begin(), outb.end()), cost(), best);
+    }
+}
+
 // digits of the top position dealt round-robin in order of decreasing level: every rank gets a similar mix of
 // levels (= a similar share of every wave) and a similar number of splits
 static int shard_assignment(const kp_plan *p, int world, uint8_t *owner, uint8_t *slot, uint32_t *nslots_of_rank)
@@ -876,6 +982,7 @@ int kp_shard_create(kp_plan *p, int rank, int world, int replicate, kp_shard **o
             cell_owner.assign((size_t)r1 * r2, 0);
             for (int d1 = 0; d1 < r1; d1++)
                 for (int d2 = 0; d2 < r2; d2++) cell_owner[(size_t)d2 + (size_t)r2 * d1] = (uint8_t)((i1[d1] + i2[d2]) % world);
+            if (world > 2 && !getenv("KP_SHARD_MODULAR")) optimise_cell_owners(t, e, e2, world, cell_owner);
             for (int d1 = 0; d1 < r1; d1++)
                 for (int d2 = 0; d2 < r2; d2++) {
                     const size_t c = (size_t)d2 + (size_t)r2 * d1;

@@ -321,6 +321,7 @@ struct KpDpParams {
     int leaf_wave;              // wave 0: rows of level 0 hold k-mers at the single-nucleotide digits
     int pf_dist;                // L2 prefetch distance of the child-tile stream, in (32 rows x 1 split) steps
     int evict_top;              // child tiles along the top `evict_top` high positions are loaded with an L2 evict-first policy
+    int pf_top;                 // only the splits of the top `pf_top` high positions are prefetched into L2 (<= 0: all of them)
     const long long *e0, *e1;   // expanded counts M, U  [ntiles][tile_kmers]
     const long long *s0, *s1;   // CV job: held-out expanded counts, subtracted on the fly (train = total - held-out); else null
     double alpha, beta, penalty;
@@ -446,6 +447,11 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
                 const int first = nhigh - p.evict_top;
                 const int ptop_ = p.evict_top > 0 ? __shfl_sync(0xffffffffu, off, first > 0 ? first : 0) : 0x7fffffff;
                 if (lane == 0) s_nhs[1] = ptop_;
+                // first split that gets an L2 prefetch: the children along the LOW high positions are mostly in L2 already
+                // (sibling tiles just read them), so prefetching them only costs L2 look-ups
+                const int pfirst = nhigh - p.pf_top;
+                const int pfs_ = (p.pf_top > 0 && pfirst > 0) ? __shfl_sync(0xffffffffu, off, pfirst) : 0;
+                if (lane == 0) s_nhs[2] = pfs_;
             }
         }
         if (ONE_LAUNCH && wave > 0) {
@@ -484,6 +490,7 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
         __syncwarp();
         const int nhs = *s_nhs;
         const int ptop = (!SHARDED && !ONE_LAUNCH) ? s_nhs[1] : 0x7fffffff;
+        const int pfs = (!SHARDED && !ONE_LAUNCH) ? s_nhs[2] : 0;
         float4 *otile = (float4 *)(p.best + (size_t)ltile * stride);
         uint32_t pushm = 0;   // replicated mode: peers that will read this tile
         if (SHARD == 2) pushm = p.view.two_d ? p.view.push_mask2[tile / p.view.hw_second] : p.view.push_mask[tile / p.view.hw_top];
@@ -518,7 +525,7 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
 #define KP_FL_PREFETCH()                                                                              \
     if (pchunk < nrows) {                                                                             \
         const uint32_t ph_ = pf_hs[ps];                                                               \
-        if (pf_on && pchunk + pf_line < nrows && (!SHARDED || (int)(ph_ >> 28) == p.my_rank))         \
+        if (pf_on && ps >= pfs && pchunk + pf_line < nrows && (!SHARDED || (int)(ph_ >> 28) == p.my_rank)) \
             asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_ptr + (size_t)(SHARDED ? (ph_ & 0x0fffffffu) : ph_) * stride4 + pchunk)); \
         if (++ps == nhs) { ps = 0; pchunk += 32; }                                                    \
     }

@@ -49,7 +49,7 @@ def test_sharded_equals_unsharded(gen_pat, world, replicate):
         owner, slot = sharded.assignment(plan, world)
         assert sum(s.info.local_tiles for s in shards) == plan.info.ntiles * (world if replicate else 1)
         cells = [s.info.top_digits for s in shards]   # digits of the top position (or, replicated: (top, second) cells) owned
-        assert max(cells) - min(cells) <= (1 if not replicate else max(2, max(cells) // 5))
+        assert max(cells) - min(cells) <= (1 if not replicate else max(2, max(cells) // 4))
         for s in shards:
             s.connect_local(shards)
         sharded.run_local(shards, eM, eU, mc, alpha, beta, penalty)
