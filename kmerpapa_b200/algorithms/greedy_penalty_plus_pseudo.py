@@ -12,7 +12,7 @@ import ctypes
 import numpy as np
 
 from .. import CV_tools, iupac
-from .._native import KP_ERR_CAPACITY, KpError, check
+from .._native import KP_ERR_CAPACITY, KpError
 from ..engine import _torch, get_plan
 from ..score_utils import get_betas
 

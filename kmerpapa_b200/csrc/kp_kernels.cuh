@@ -727,9 +727,14 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
                             ru = (double)sf > s_;
                         }
                         if (ru) rupm |= 1u << d;
+                        // park the result in this row's own slot of S (its minima are in v[] since the start of the round and
+                        // the slot is rewritten by the row's final store): one 4-byte store instead of R0 predicated moves
+                        ((float *)(S + (d >> 2) * rp + srow))[d & 3] = sf;
+                    }
 #pragma unroll
-                        for (int c = 0; c < R0; c++)
-                            if (c == d) sfx[c] = sf;
+                    for (int g = 0; g < NG; g++) {
+                        const float4 x = S[g * rp + srow];
+                        sfx[4 * g] = x.x; sfx[4 * g + 1] = x.y; sfx[4 * g + 2] = x.z; sfx[4 * g + 3] = x.w;
                     }
                 }
                 // ---- register position: in-register splits + self-score compare, digit by digit.

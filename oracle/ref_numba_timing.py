@@ -18,7 +18,6 @@ import json
 import os
 import sys
 import time
-import types
 import warnings
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

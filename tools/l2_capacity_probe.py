@@ -2,7 +2,6 @@
 """How much of the 126 MB L2 does a buffer read by ALL SMs get?  Re-reads a buffer of N MB many times (torch sum over
 float32, every SM touches every part of it over time) and prints the achieved read bandwidth: far above the HBM rate while
 the buffer stays L2-resident, the HBM rate beyond.  The knee is the effective capacity for data shared by both dies."""
-import sys
 import torch
 
 torch.cuda.set_device(0)
