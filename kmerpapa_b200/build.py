@@ -6,7 +6,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_PKG, "csrc")
 SOURCES = ["kp_api.cu", "kp_plan.cpp"]
-HEADERS = ["kp_kernels.cuh", "kp_fiber.cuh", "kp_math.cuh", "kp_tables.h", "kp_plan.h", "kp_log_data.h"]
+HEADERS = ["kp_kernels.cuh", "kp_fiber.cuh", "kp_math.cuh", "kp_tables.h", "kp_plan.h", "kp_log_data.h", "kp_shard_owners.h"]
 OUT = os.path.join(_PKG, "libkpapa.so")
 
 NVCC_FLAGS = [
