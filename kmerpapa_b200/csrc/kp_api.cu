@@ -983,11 +983,11 @@ int kp_shard_create(kp_plan *p, int rank, int world, int replicate, kp_shard **o
             cell_owner.assign((size_t)r1 * r2, 0);
             for (int d1 = 0; d1 < r1; d1++)
                 for (int d2 = 0; d2 < r2; d2++) cell_owner[(size_t)d2 + (size_t)r2 * d1] = (uint8_t)((i1[d1] + i2[d2]) % world);
-            if (world > 2 && !getenv("KP_SHARD_MODULAR")) {
+            if (world > 1 && !getenv("KP_SHARD_MODULAR")) {
                 if (r1 == 15 && r2 == 15 && world <= 8 && !getenv("KP_SHARD_SEARCH")) {
                     // two N positions: tables found offline by a longer run of the same search (tools/optimise_shard_owners.py)
                     for (int d1 = 0; d1 < 15; d1++)
-                        for (int d2 = 0; d2 < 15; d2++) cell_owner[(size_t)d2 + 15u * d1] = kp_shard_owner_tab[world - 3][d1][d2];
+                        for (int d2 = 0; d2 < 15; d2++) cell_owner[(size_t)d2 + 15u * d1] = kp_shard_owner_tab[world - 2][d1][d2];
                 } else {
                     optimise_cell_owners(t, e, e2, world, cell_owner);
                 }

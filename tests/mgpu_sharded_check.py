@@ -13,6 +13,24 @@ from kmerpapa_b200 import sharded, synthetic
 from kmerpapa_b200.engine import get_plan
 
 
+def nvlink_bytes(index):
+    """(received, sent) bytes over all NVLink links of physical GPU `index` so far (NVML field values), or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        rx = pynvml.nvmlDeviceGetFieldValues(h, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])[0]
+        tx = pynvml.nvmlDeviceGetFieldValues(h, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF)])[0]
+        if rx.nvmlReturn != 0 or tx.nvmlReturn != 0:
+            return None
+        return int(rx.value.ullVal) * 1024, int(tx.value.ullVal) * 1024     # the counters are in KiB
+    except Exception:
+        return None
+
+
 def main():
     gen_pat = sys.argv[1] if len(sys.argv) > 1 else "NNNNANNN"
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
@@ -31,6 +49,7 @@ def main():
     sh = sharded.ShardedDP(plan, rank, world, replicate=replicate)
     sh.connect()
     ms = []
+    nv0 = nvlink_bytes(local)
     for rep in range(reps):
         sh.barrier()
         torch.cuda.synchronize()
@@ -42,6 +61,16 @@ def main():
         t = torch.tensor([e0.elapsed_time(e1)], device=plan.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms.append(float(t.item()))
+    nv1 = nvlink_bytes(local)
+    if nv0 is not None and nv1 is not None:   # NVLink traffic of the DPs alone (the reads of the backtrack come after)
+        t = torch.tensor([(nv1[0] - nv0[0]) / reps, (nv1[1] - nv0[1]) / reps], dtype=torch.float64, device=plan.device)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        if rank == 0:
+            rx = [float(x[0]) / 1e9 for x in allt]
+            tx = [float(x[1]) / 1e9 for x in allt]
+            print("NVLink GB per DP and rank (NVML throughput counters): received " + " ".join(f"{x:.2f}" for x in rx) +
+                  " | sent " + " ".join(f"{x:.2f}" for x in tx) + f" | busiest receiver {max(rx):.2f} GB", flush=True)
     part = sh.backtrack()
     top = sh.top_score()
     # size-independent properties of the result (the only checks available when the table exceeds one GPU):
