@@ -167,7 +167,6 @@ __global__ void __launch_bounds__(KP_FIBER_THREADS, 1) kp_dp_fiber_kernel(const 
         fsplit[240 + d] = (uint8_t)ns;
     }
     __syncthreads();
-    const uint8_t *srow_of_frow = blob + ft.ft_srow_of_frow;
     const uint8_t *frow_of_srow = blob + ft.ft_frow_of_srow;
     const uint16_t *xs_off = (const uint16_t *)(blob + ft.ft_xs_off);
     const uint16_t *xs = (const uint16_t *)(blob + ft.ft_xs);

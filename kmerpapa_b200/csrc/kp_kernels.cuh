@@ -239,10 +239,16 @@ __device__ __forceinline__ float kp_min3(float a, float b, float c)
 }
 
 // Float32 lower bound of the self-score (w_numba.py:56-61) for the score filter, two patterns at a time with
-// the packed f32x2 instructions of sm_100 (FADD2/FMUL2/FFMA2).  Error budget of the estimate: counts -> float32 and
-// the arithmetic, relative < 1e-5 of |s| (no cancellation: both terms are >= 0; log(1-p) by its series below
-// p = 2^-5); __logf, ABSOLUTE 2^-21.4 for arguments in [0.5, 2] (rates near 1, or 1-p near 1 above the series range),
-// i.e. up to 2 * 3.6e-7 * (M + U) in s.  The bound subtracts 2e-4 |s| + 1e-6 (M + U) + 0.01.
+// the packed f32x2 instructions of sm_100 (FADD2/FMUL2/FFMA2).  Error budget of the estimate (both terms of s are >= 0:
+// no cancellation):
+//   counts -> float32 and their sums   <= 4 roundings of 2^-24 on M, U           (exact below 2^24)
+//   p = (M + a) / (M + U + a + b)      <= 2 roundings + __fdividef (2 ulp):  |dp| / p <= 2.4e-7 + conversions 3.6e-7 = 6e-7
+//   p < 2^-5 (the usual case):  ln p < -3.4, so  __logf  is in its RELATIVE regime (3 ulp) and the error of p adds
+//       6e-7 / 3.4 relative: 5.5e-7 of the first term; ln(1-p) by its series (truncation p^4/5 < 2e-7, three roundings) plus the
+//       error of p: 1e-6 of the second term; the final fma / mul / add: 2e-7.   Total < 1.5e-6 |s|;  bound used: 1e-5 |s| + 0.01.
+//   p >= 2^-5:  __logf has ABSOLUTE error 2^-21.4 = 3.6e-7 for arguments in [0.5, 2] (rates near 1, or 1-p above the series
+//       range), and the error of p enters ln p and ln(1-p) absolutely (up to 6e-7 / 0.5): together < 1.6e-6 per unit of count,
+//       times 2: bound used  2e-4 |s| + 4e-6 (M + U) + 0.01.
 // A NaN (p == 0, ...) never skips the exact score.
 __device__ __forceinline__ float2 kp_score_lower_bound2(float2 Mf, float2 Uf, float alpha, float ab, float penalty)
 {
@@ -256,13 +262,12 @@ __device__ __forceinline__ float2 kp_score_lower_bound2(float2 Mf, float2 Uf, fl
     t = __ffma2_rn(p, t, make_float2(0.5f, 0.5f));
     t = __ffma2_rn(p, t, make_float2(1.0f, 1.0f));
     float2 l1 = __fmul2_rn(make_float2(-p.x, -p.y), t);
-    if (!(p.x < 0.03125f)) l1.x = __logf(1.0f - p.x);
-    if (!(p.y < 0.03125f)) l1.y = __logf(1.0f - p.y);
+    float2 rel = make_float2(1e-5f, 1e-5f), per = make_float2(0.f, 0.f);   // margin: relative only for small rates
+    if (!(p.x < 0.03125f)) { l1.x = __logf(1.0f - p.x); rel.x = 2e-4f; per.x = 4e-6f; }
+    if (!(p.y < 0.03125f)) { l1.y = __logf(1.0f - p.y); rel.y = 2e-4f; per.y = 4e-6f; }
     const float2 ll = __ffma2_rn(Mf, lp, __fmul2_rn(Uf, l1));                       // M log p + U log(1-p)  (<= 0)
     const float2 est = __ffma2_rn(ll, make_float2(-2.0f, -2.0f), make_float2(penalty, penalty));
-    // est - (2e-4 |est| + 1e-6 (M + U) + 0.01)
-    const float2 mar = __ffma2_rn(make_float2(fabsf(est.x), fabsf(est.y)), make_float2(2e-4f, 2e-4f),
-                                  __ffma2_rn(cnt, make_float2(1e-6f, 1e-6f), make_float2(0.01f, 0.01f)));
+    const float2 mar = __ffma2_rn(make_float2(fabsf(est.x), fabsf(est.y)), rel, __ffma2_rn(cnt, per, make_float2(0.01f, 0.01f)));
     return __fadd2_rn(est, make_float2(-mar.x, -mar.y));
 }
 
