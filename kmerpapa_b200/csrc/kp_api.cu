@@ -77,6 +77,7 @@ struct kp_plan {
     bool use_fiber = false;          // KP_DP_KERNEL=fiber|rows: which kernel family runs the unsharded DP
     int pf_dist = KP_PF_DIST;        // KP_PF_DIST: L2 prefetch distance of the child-tile stream
     int evict_top = KP_EVICT_TOP;    // KP_EVICT_TOP: top high positions whose child tiles are loaded L2-evict-first
+    int pf_bulk = 0;                 // KP_PF_BULK=1: L2 prefetch by bulk copies (UBLKPF) instead of one line per lane
     int pf_top = KP_PF_TOP;          // KP_PF_TOP: only the splits of this many top high positions are prefetched (0: all)
     bool one_launch = false;         // KP_ONE_LAUNCH=1: all waves in one launch
 };
@@ -220,6 +221,7 @@ static int plan_create(const char *gen_pat, int device, bool lattice, kp_plan **
     if (const char *e = getenv("KP_PF_DIST")) p->pf_dist = atoi(e);
     if (const char *e = getenv("KP_EVICT_TOP")) p->evict_top = atoi(e);
     if (const char *e = getenv("KP_PF_TOP")) p->pf_top = atoi(e);
+    if (const char *e = getenv("KP_PF_BULK")) p->pf_bulk = atoi(e);
     if (const char *e = getenv("KP_ONE_LAUNCH")) p->one_launch = e[0] == '1';
     for (int wide = 0; wide < 2; wide++) {
         size_t fixed = 2048 + t.rt_bytes, per_warp = t.warp_smem_bytes[wide];
@@ -500,6 +502,7 @@ static int dp_counts(kp_plan *p, const int64_t *d_expM, const int64_t *d_expU, c
     prm.pf_dist = p->pf_dist;
     prm.evict_top = p->evict_top < p->host.t.nhigh ? p->evict_top : 0;
     prm.pf_top = p->pf_top;
+    prm.pf_bulk = p->pf_bulk;
     return launch_dp(p, wide, prm, (cudaStream_t)stream);
 }
 

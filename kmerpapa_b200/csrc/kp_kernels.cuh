@@ -327,6 +327,7 @@ struct KpDpParams {
     int pf_dist;                // L2 prefetch distance of the child-tile stream, in (32 rows x 1 split) steps
     int evict_top;              // child tiles along the top `evict_top` high positions are loaded with an L2 evict-first policy
     int pf_top;                 // only the splits of the top `pf_top` high positions are prefetched into L2 (<= 0: all of them)
+    int pf_bulk;                // L2 prefetch by bulk copies (cp.async.bulk.prefetch.L2, one per 512-byte segment) instead of one line per lane
     const long long *e0, *e1;   // expanded counts M, U  [ntiles][tile_kmers]
     const long long *s0, *s1;   // CV job: held-out expanded counts, subtracted on the fly (train = total - held-out); else null
     double alpha, beta, penalty;
@@ -526,12 +527,24 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
             const uint32_t *pf_hs = (lane & 16) ? hs2 : hs1;
             const int pf_g = (lane >> 2) & 3, pf_line = (lane & 3) * 8;
             const float4 *pf_ptr = tb4 + pf_g * rp + pf_line;
-            const bool pf_on = pf_g < NG && p.pf_dist >= 0;   // KP_PF_DIST < 0: no L2 prefetch at all
+            const bool pf_bulk = p.pf_bulk != 0;
+            const bool pf_on = (pf_bulk || pf_g < NG) && p.pf_dist >= 0;   // KP_PF_DIST < 0: no L2 prefetch at all
 #define KP_FL_PREFETCH()                                                                              \
     if (pchunk < nrows) {                                                                             \
-        const uint32_t ph_ = pf_hs[ps];                                                               \
-        if (pf_on && ps >= pfs && pchunk + pf_line < nrows && (!SHARDED || (int)(ph_ >> 28) == p.my_rank)) \
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_ptr + (size_t)(SHARDED ? (ph_ & 0x0fffffffu) : ph_) * stride4 + pchunk)); \
+        if (!SHARDED && pf_bulk) {   /* one bulk L2 prefetch (UBLKPF) per 512-byte segment: warp-uniform addresses */ \
+            if (pf_on && ps >= pfs) {                                                                 \
+                const uint32_t nb_ = (uint32_t)(nrows - pchunk < 32 ? nrows - pchunk : 32) * 16u;     \
+                const float4 *c1_ = tb4 + (size_t)hs1[ps] * stride4 + pchunk, *c2_ = tb4 + (size_t)hs2[ps] * stride4 + pchunk; \
+                _Pragma("unroll") for (int g = 0; g < NG; g++) {                                      \
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(c1_ + g * rp), "r"(nb_)); \
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(c2_ + g * rp), "r"(nb_)); \
+                }                                                                                     \
+            }                                                                                         \
+        } else {                                                                                      \
+            const uint32_t ph_ = pf_hs[ps];                                                           \
+            if (pf_on && ps >= pfs && pchunk + pf_line < nrows && (!SHARDED || (int)(ph_ >> 28) == p.my_rank)) \
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_ptr + (size_t)(SHARDED ? (ph_ & 0x0fffffffu) : ph_) * stride4 + pchunk)); \
+        }                                                                                             \
         if (++ps == nhs) { ps = 0; pchunk += 32; }                                                    \
     }
 #define KP_FL_LOAD(xa, xb)                                                                            \
