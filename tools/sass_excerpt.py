@@ -25,7 +25,7 @@ def mix(ins):
     c = collections.Counter()
     for _, t in ins:
         op = t.split()[1] if t.startswith("@") else t.split()[0]
-        c[".".join(op.split(".")[:3]) if op.startswith(("LDG", "STG", "LDS", "STS", "MUFU", "UBLKCP", "UTMA", "LDGSTS")) else op.split(".")[0]] += 1
+        c[".".join(op.split(".")[:3]) if op.startswith(("LDG", "STG", "LDS", "STS", "MUFU", "UBLKCP", "UBLKPF", "UTMA", "LDGSTS")) else op.split(".")[0]] += 1
     return c
 
 
@@ -40,11 +40,11 @@ for name, fun in KERNELS.items():
     c = mix(ins)
     print(f"\n## kp_dp_{name}_kernel: {len(ins)} instructions (with its out-of-line device functions)")
     keys = ["LDG.E.128", "STG.E.128", "LDS.128", "STS.128", "FADD2", "FFMA2", "FMUL2", "FMNMX", "FMNMX3", "FADD", "DFMA", "DADD", "DMUL",
-            "DSETP", "MUFU.RCP64H", "MUFU.LG2", "MUFU.RCP", "I2F", "F2F", "BAR", "CALL", "UBLKCP", "UTMALDG", "UTMASTG", "LDGSTS", "STL", "LDL"]
+            "DSETP", "MUFU.RCP64H", "MUFU.LG2", "MUFU.RCP", "I2F", "F2F", "BAR", "CALL", "UBLKPF", "UBLKCP", "UTMALDG", "UTMASTG", "LDGSTS", "STL", "LDL"]
     print("   ", ", ".join(f"{k} {sum(v for kk, v in c.items() if kk == k or kk.startswith(k + '.'))}" for k in keys))
     if name == "rows":
         print("\n### child-tile stream (phase D): eight LDG.128 per step with immediate group offsets, packed FADD2, FMNMX")
-        print(excerpt(ins, lambda t: t.startswith("LDG.E.128.CONSTANT"), 64))
+        print(excerpt(ins, lambda t: "LDG.E.128" in t, 64))
         print("\n### fast self-score (kp_self_score_fast): reciprocal seed + two Newton steps, table log, Horner log(1-p), error bound")
         print(excerpt(ins, lambda t: "MUFU.RCP64H" in t, 96))
     else:
