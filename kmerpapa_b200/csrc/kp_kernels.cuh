@@ -46,6 +46,12 @@
 #ifndef KP_PIPE_DEPTH
 #define KP_PIPE_DEPTH 2      // register stages of the child-tile stream (3 needs <= 13 warps for its registers)
 #endif
+// Experimental variants of the child-tile stream measured in round 2 and found not to help (profiles/r02_l2_experiments.txt):
+// L2 evict-first policy loads for the top positions' children (KP_EVICT_TOP), prefetch of the top positions' splits only
+// (KP_PF_TOP), bulk L2 prefetch (KP_PF_BULK).  Compiled in only with -DKP_EXPERIMENTS=1: they lengthen the hot loop's code.
+#ifndef KP_EXPERIMENTS
+#define KP_EXPERIMENTS 0
+#endif
 #ifndef KP_PF_DIST
 #define KP_PF_DIST 2         // L2 prefetch distance of the child-tile stream, in (32 rows x 1 split) steps
 #endif
@@ -449,7 +455,7 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
                 }
             }
             if (lane == 0) *s_nhs = total;
-            if (!SHARDED && !ONE_LAUNCH) {   // first split of the top `evict_top` positions (the list is in position order)
+            if (KP_EXPERIMENTS && !SHARDED && !ONE_LAUNCH) {   // first split of the top `evict_top` positions (the list is in position order)
                 const int first = nhigh - p.evict_top;
                 const int ptop_ = p.evict_top > 0 ? __shfl_sync(0xffffffffu, off, first > 0 ? first : 0) : 0x7fffffff;
                 if (lane == 0) s_nhs[1] = ptop_;
@@ -495,8 +501,8 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
         }
         __syncwarp();
         const int nhs = *s_nhs;
-        const int ptop = (!SHARDED && !ONE_LAUNCH) ? s_nhs[1] : 0x7fffffff;
-        const int pfs = (!SHARDED && !ONE_LAUNCH) ? s_nhs[2] : 0;
+        const int ptop = (KP_EXPERIMENTS && !SHARDED && !ONE_LAUNCH) ? s_nhs[1] : 0x7fffffff;
+        const int pfs = (KP_EXPERIMENTS && !SHARDED && !ONE_LAUNCH) ? s_nhs[2] : 0;
         float4 *otile = (float4 *)(p.best + (size_t)ltile * stride);
         uint32_t pushm = 0;   // replicated mode: peers that will read this tile
         if (SHARD == 2) pushm = p.view.two_d ? p.view.push_mask2[tile / p.view.hw_second] : p.view.push_mask[tile / p.view.hw_top];
@@ -527,11 +533,11 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
             const uint32_t *pf_hs = (lane & 16) ? hs2 : hs1;
             const int pf_g = (lane >> 2) & 3, pf_line = (lane & 3) * 8;
             const float4 *pf_ptr = tb4 + pf_g * rp + pf_line;
-            const bool pf_bulk = p.pf_bulk != 0;
+            const bool pf_bulk = KP_EXPERIMENTS && p.pf_bulk != 0;
             const bool pf_on = (pf_bulk || pf_g < NG) && p.pf_dist >= 0;   // KP_PF_DIST < 0: no L2 prefetch at all
 #define KP_FL_PREFETCH()                                                                              \
     if (pchunk < nrows) {                                                                             \
-        if (!SHARDED && pf_bulk) {   /* one bulk L2 prefetch (UBLKPF) per 512-byte segment: warp-uniform addresses */ \
+        if (KP_EXPERIMENTS && !SHARDED && pf_bulk) {   /* one bulk L2 prefetch (UBLKPF) per 512-byte segment: warp-uniform addresses */ \
             if (pf_on && ps >= pfs) {                                                                 \
                 const uint32_t nb_ = (uint32_t)(nrows - pchunk < 32 ? nrows - pchunk : 32) * 16u;     \
                 const float4 *c1_ = tb4 + (size_t)hs1[ps] * stride4 + pchunk, *c2_ = tb4 + (size_t)hs2[ps] * stride4 + pchunk; \
@@ -559,7 +565,7 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
             a_ = (const float4 *)p.view.best[h1_ >> 28] + lrowc + (size_t)(h1_ & 0x0fffffffu) * stride4; \
             b_ = (const float4 *)p.view.best[h2_ >> 28] + lrowc + (size_t)(h2_ & 0x0fffffffu) * stride4; \
         }                                                                                             \
-        if (!SHARDED && !ONE_LAUNCH && ls >= ptop) {   /* warp-uniform: no sibling will find these lines in L2 */ \
+        if (KP_EXPERIMENTS && !SHARDED && !ONE_LAUNCH && ls >= ptop) {   /* warp-uniform: no sibling will find these lines in L2 */ \
             _Pragma("unroll") for (int g = 0; g < NG; g++) {                                          \
                 xa[g] = kp_ldg_policy(a_ + g * rp, pol_first);                                        \
                 xb[g] = kp_ldg_policy(b_ + g * rp, pol_first);                                        \
