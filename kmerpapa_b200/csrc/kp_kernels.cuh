@@ -108,8 +108,11 @@ __device__ __noinline__ double kp_self_score_exact_nl(C M, C U, double alpha, do
 //   mul / add       four roundings in each sequence                                                -> 2^-50 a
 //   total           < 2^-48 a + 2^-51 (M + U);   the bound used is  eps = 2^-46 a + 2^-49 (M + U).
 // Returns false when the arguments are outside the window above (the caller then takes the exact path).
+#ifndef KP_FAST_INLINE
+#define KP_FAST_INLINE __forceinline__
+#endif
 template <typename C>
-__device__ __forceinline__ bool kp_self_score_fast(C M, C U, double alpha, double beta, double penalty, const double2 *tab,
+__device__ KP_FAST_INLINE bool kp_self_score_fast(C M, C U, double alpha, double beta, double penalty, const double2 *tab,
                                                    const KpLogK &K, float &sf, bool &rup)
 {
     const double Md = kp_cnt2d(M), Ud = kp_cnt2d(U), Sd = kp_cnt2d((C)(M + U));
