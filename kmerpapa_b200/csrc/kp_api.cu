@@ -77,6 +77,7 @@ struct kp_plan {
     bool use_fiber = false;          // KP_DP_KERNEL=fiber|rows: which kernel family runs the unsharded DP
     int pf_dist = KP_PF_DIST;        // KP_PF_DIST: L2 prefetch distance of the child-tile stream
     int evict_top = KP_EVICT_TOP;    // KP_EVICT_TOP: top high positions whose child tiles are loaded L2-evict-first
+    bool coop_tail = true;           // KP_NO_COOP_TAIL: waves of at most one tile per SM run one CTA per tile (all warps stream)
     int pf_bulk = 0;                 // KP_PF_BULK=1: L2 prefetch by bulk copies (UBLKPF) instead of one line per lane
     int pf_top = KP_PF_TOP;          // KP_PF_TOP: only the splits of this many top high positions are prefetched (0: all)
     bool one_launch = false;         // KP_ONE_LAUNCH=1: all waves in one launch
@@ -222,6 +223,7 @@ static int plan_create(const char *gen_pat, int device, bool lattice, kp_plan **
     if (const char *e = getenv("KP_EVICT_TOP")) p->evict_top = atoi(e);
     if (const char *e = getenv("KP_PF_TOP")) p->pf_top = atoi(e);
     if (const char *e = getenv("KP_PF_BULK")) p->pf_bulk = atoi(e);
+    if (getenv("KP_NO_COOP_TAIL")) p->coop_tail = false;
     if (const char *e = getenv("KP_ONE_LAUNCH")) p->one_launch = e[0] == '1';
     for (int wide = 0; wide < 2; wide++) {
         size_t fixed = 2048 + t.rt_bytes, per_warp = t.warp_smem_bytes[wide];
@@ -449,6 +451,16 @@ static int launch_dp(kp_plan *p, bool wide, KpDpParams prm, cudaStream_t st)
         prm.counter = p->d_counters + l;
         prm.leaf_wave = (l == 0);
         uint64_t ntile = hi - lo;
+        const int nchunk = (t.nrows + 31) / 32;
+        if (p->coop_tail && t.r0 == 15 && ntile <= (uint64_t)p->sm_count && nchunk <= KP_MAX_WARPS) {
+            // at most one tile per SM (the last waves of a big lattice, every wave of a small one): a CTA per tile, every
+            // warp streams one 32-row chunk of it, warp 0 runs the rounds - the wave costs a fraction of a tile latency
+            const size_t smc = 2048 + t.rt_bytes + (size_t)t.warp_smem_bytes[wide];
+            if (t.rp == KP_RP_NN) launch_dp_r0<15, KP_RP_NN, 4>(wide, (int)ntile, nchunk * 32, smc, st, prm);
+            else launch_dp_r0<15, 0, 4>(wide, (int)ntile, nchunk * 32, smc, st, prm);
+            p->launches++;
+            continue;
+        }
         int warps = nw;
         if (ntile < (uint64_t)p->sm_count * nw) {  // small wave: spread the tiles over all SMs
             warps = (int)((ntile + p->sm_count - 1) / p->sm_count);

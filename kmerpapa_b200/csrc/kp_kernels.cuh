@@ -374,6 +374,7 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
     constexpr int NB = R0 == 15 ? 4 : (R0 == 7 ? 3 : (R0 == 3 ? 2 : 1));
     constexpr bool SHARDED = SHARD == 1;   // partitioned addressing
     constexpr bool ONE_LAUNCH = SHARD == 3;
+    constexpr bool COOP = SHARD == 4;      // one tile per CTA: every warp streams one 32-row chunk, warp 0 runs the rounds
 
     extern __shared__ __align__(16) unsigned char smem[];
     const KpTables &tb = *p.tab;
@@ -395,7 +396,7 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
     const uint16_t *bs_off = (const uint16_t *)(rt + tb.rt_bs_off);
     const uint16_t *bs = (const uint16_t *)(rt + tb.rt_bs);
 
-    unsigned char *wm = smem + 2048 + rt_bytes + (size_t)warp * tb.warp_smem_bytes[WIDE];
+    unsigned char *wm = smem + 2048 + rt_bytes + (size_t)(COOP ? 0 : warp) * tb.warp_smem_bytes[WIDE];
     float4 *S = (float4 *)wm;                                  // [NG][rp] the warp's copy of its tile
     C *bc = (C *)(wm + (size_t)NG * rp * 16);                  // [tile_kmers][2] base counts of the tile
     uint32_t *hs1 = (uint32_t *)((unsigned char *)bc + (size_t)tk * 2 * sizeof(C));
@@ -412,8 +413,15 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
     // always neighbours in the pattern lattice, which share child tiles, so those re-reads hit in L2.
     for (;;) {
         uint32_t it = 0;
-        if (lane == 0) it = atomicAdd(p.counter, 1u);
-        it = __shfl_sync(0xffffffffu, it, 0);
+        if (COOP) {   // the CTA claims: all warps have left the previous tile, then one thread takes the next
+            __syncthreads();
+            if (threadIdx.x == 0) s_nhs[3] = (int)atomicAdd(p.counter, 1u);
+            __syncthreads();
+            it = (uint32_t)s_nhs[3];
+        } else {
+            if (lane == 0) it = atomicAdd(p.counter, 1u);
+            it = __shfl_sync(0xffffffffu, it, 0);
+        }
         if (it >= p.ntiles_wave) break;
         const uint32_t tile = p.tile_list[it];
         const int wave = ONE_LAUNCH ? (int)p.tile_wave[it] : 0;
@@ -425,7 +433,7 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
         }
         __syncwarp();  // previous tile's readers of S / bc / hs are done
         // ---- the tile's high-position splits (two child tiles each) ----
-        {
+        if (!COOP || warp == 0) {
             int ns = 0, d = 0, e = 0;
             uint32_t m = 0, hw = 1;
             if (lane < nhigh) {
@@ -497,12 +505,13 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
             }
         }
         // ---- base counts of the tile ----
-        for (uint32_t kl = lane; kl < tk; kl += 32) {
+        for (uint32_t kl = COOP ? threadIdx.x : lane; kl < tk; kl += COOP ? blockDim.x : 32) {
             size_t g = (size_t)tile * tk + kl;
             bc[kl * 2 + 0] = (C)(p.s0 ? p.e0[g] - p.s0[g] : p.e0[g]);
             bc[kl * 2 + 1] = (C)(p.s1 ? p.e1[g] - p.s1[g] : p.e1[g]);
         }
         __syncwarp();
+        if (COOP) __syncthreads();   // split list (warp 0) and base counts (all warps) are in place
         const int nhs = *s_nhs;
         const int ptop = (KP_EXPERIMENTS && !SHARDED && !ONE_LAUNCH) ? s_nhs[1] : 0x7fffffff;
         const int pfs = (KP_EXPERIMENTS && !SHARDED && !ONE_LAUNCH) ? s_nhs[2] : 0;
@@ -518,7 +527,10 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
             float v[NG * 4];
 #pragma unroll
             for (int c = 0; c < NG * 4; c++) v[c] = INF;
-            const int nchunk = (nrows + 31) >> 5;
+            const int nchunk_all = (nrows + 31) >> 5;
+            const int chunk0 = COOP ? warp : 0;                                   // first 32-row chunk this warp streams
+            const int nchunk = COOP ? (warp < nchunk_all ? 1 : 0) : nchunk_all;   // ... and how many
+            const int pend = COOP ? (nrows < 32 * (chunk0 + 1) ? nrows : 32 * (chunk0 + 1)) : nrows;   // end of its rows
             const int nstep = nhs > 0 ? nchunk * nhs : 0;
             float4 xa0[NG], xb0[NG], xa1[NG], xb1[NG];
 #if KP_PIPE_DEPTH == 3
@@ -526,20 +538,20 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
 #endif
             const float4 *tb4 = (const float4 *)tbase;
             const uint32_t stride4 = stride >> 2;                 // tile stride in float4
-            int ls = 0, lrow = lane;          // split and row of the next load
+            int ls = 0, lrow = lane + 32 * chunk0;          // split and row of the next load
             const float4 *lptr = tb4 + (lrow < nrows ? lrow : nrows - 1);   // idle lanes of the last chunk re-read a valid row
             int lrowc = lrow < nrows ? lrow : nrows - 1;                    // (sharded: the row, the base depends on the owner)
-            int us = 0, urow = lane;          // split and row of the next use
+            int us = 0, urow = lane + 32 * chunk0;          // split and row of the next use
             // register-free deepening of the pipeline: every step also asks L2 for the lines of a later step.
             // One prefetch per step: the 2 x NG x 4 lines (128 B = 8 rows) of a step map onto the 32 lanes.
-            int ps = 0, pchunk = 0;           // split and first row of the next L2 prefetch (pf_dist steps ahead)
+            int ps = 0, pchunk = 32 * chunk0;   // split and first row of the next L2 prefetch (pf_dist steps ahead)
             const uint32_t *pf_hs = (lane & 16) ? hs2 : hs1;
             const int pf_g = (lane >> 2) & 3, pf_line = (lane & 3) * 8;
             const float4 *pf_ptr = tb4 + pf_g * rp + pf_line;
             const bool pf_bulk = KP_EXPERIMENTS && p.pf_bulk != 0;
             const bool pf_on = (pf_bulk || pf_g < NG) && p.pf_dist >= 0;   // KP_PF_DIST < 0: no L2 prefetch at all
 #define KP_FL_PREFETCH()                                                                              \
-    if (pchunk < nrows) {                                                                             \
+    if (pchunk < pend) {                                                                              \
         if (KP_EXPERIMENTS && !SHARDED && pf_bulk) {   /* one bulk L2 prefetch (UBLKPF) per 512-byte segment: warp-uniform addresses */ \
             if (pf_on && ps >= pfs) {                                                                 \
                 const uint32_t nb_ = (uint32_t)(nrows - pchunk < 32 ? nrows - pchunk : 32) * 16u;     \
@@ -635,16 +647,17 @@ __global__ void KP_DP_BOUNDS kp_dp_rows_kernel(const KpDpParams p)
 #undef KP_FL_LOAD
 #undef KP_FL_USE
 #undef KP_FL_PREFETCH
-            if (nstep == 0)  // no high-position split (wave 0, or a pattern without high positions)
-                for (int srow = lane; srow < nrows; srow += 32) {
+            if (nhs <= 0)  // no high-position split (wave 0, or a pattern without high positions)
+                for (int srow = COOP ? (int)threadIdx.x : lane; srow < nrows; srow += COOP ? (int)blockDim.x : 32) {
 #pragma unroll
                     for (int g = 0; g < NG; g++) S[g * rp + srow] = make_float4(INF, INF, INF, INF);
                 }
             __syncwarp();
+            if (COOP) __syncthreads();   // every chunk's minima are parked
         }
 
         // ---- rounds ----
-        for (int rnd = 0; rnd < nrounds; rnd++) {
+        for (int rnd = 0; rnd < (COOP && warp != 0 ? 0 : nrounds); rnd++) {
             const int srow = round_start[rnd] + lane;
             if (srow < round_start[rnd + 1]) {
                 float v[NG * 4];
