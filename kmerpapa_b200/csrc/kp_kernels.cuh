@@ -16,8 +16,9 @@
 //                 pattern whose estimate minus margin already exceeds its best split so far can never be
 //                 kept whole (later in-register splits only lower the best split), so its exact score is
 //                 never needed;
-//                 EXACT SCORE for the remaining patterns only: float64, glibc-exact log (kp_math.cuh), in a
-//                 rolled loop (the code exists once); RN_f32(s) and a "rounded up" bit are kept, because
+//                 SCORE for the remaining patterns only, in a rolled loop (the code exists once): a fast float64
+//                 evaluation with a rigorous error bound (kp_self_score_fast) decides RN_f32(s) and the "rounded up"
+//                 bit for all but about one score in 10^5, which take the glibc-exact path (kp_math.cuh); both are kept because
 //                 the reference's float64 compare  s < (double)best  is exactly
 //                 sf < best || (sf == best && rounded_up), and the value it stores on a win is sf;
 //                 in-register splits of the register position interleaved with that compare, fully
@@ -361,6 +362,9 @@ struct KpDpParams {
 //     rank in their top 4 bits).
 //   2 (replicated, speed): every rank holds a full-size table; a finished row is stored locally AND into the
 //     table of every peer that owns a superset digit (posted NVLink writes), so all reads stay local.
+//   4 (one GPU, small waves): at most one tile per SM in the wave (the last waves of a big lattice, every wave of a small one).
+//     A CTA owns one tile: each of its warps streams ONE 32-row chunk of the child tiles into the shared copy, then warp 0
+//     runs the rounds; the wave then costs a fraction of a tile latency instead of a whole one.
 //   3 (one GPU, single launch; opt-in): tile_list holds every wave back to back and tiles are claimed in that order by
 //     the resident warps (one CTA per SM, all resident); a tile spins until its child tiles are flagged done.  Claiming
 //     in order makes this deadlock-free: every child was claimed earlier, by a warp that is running.  The table is then
