@@ -247,3 +247,31 @@ def test_a_sublattice_is_a_dp_of_its_own(oracle):
         assert np.array_equal(full["score"][nums].view(np.uint32), ref["score"].view(np.uint32))
         assert np.array_equal(full["split"][nums], ref["split"])
         assert np.array_equal(full["M"][nums], ref["M"])
+
+
+def test_bench_config_is_shared_by_both_arms_and_goldens_are_checked():
+    """bench.py: both arms print the same `config` object; a result that differs from the full-size golden aborts."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("kp_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for name in ("cfg3", "cfg4", "cfg5", "n9m"):
+        a, b = bench.config_for(name, 1), bench.config_for(name, 1)
+        assert a == b and json.loads(json.dumps(a)) == a and "workload" in a and "model" not in a
+    assert bench.config_for("cfg3", 1)["npat"] == 2562890625 and bench.config_for("cfg5", 1)["npat"] == 922640625
+    assert bench.host_threads() >= 1
+    g = bench.golden("cfg4")
+    assert g is not None and len(g["jobs_run"]) == 45 and g["selected"][:2] == [10.0, 6.0]
+    res = np.array([int(x, 16) for x in g["job_bits"]], dtype=np.uint32).view(np.float32).reshape(1, 5, 3, 3, 2)
+    best = (g["selected"][0], g["selected"][1], np.float32(g["selected"][2]))
+    out = bench.check_cv_against_golden(res, best)
+    assert out["checked"] and out["jobs_compared"] == 45 and out["selected_compared"]
+    bad = res.copy()
+    bad[0, 2, 1, 1, 1] = np.nextafter(bad[0, 2, 1, 1, 1], np.float32(0))
+    with pytest.raises(AssertionError):
+        bench.check_cv_against_golden(bad, best)
+    g3 = bench.golden("cfg3")
+    with pytest.raises(AssertionError):
+        bench.check_single_against_golden("cfg3", np.float32(g3["loss"]) + np.float32(8.0), np.zeros(g3["partition_patterns"], dtype=np.uint64))
+    assert bench.check_single_against_golden("n9m", np.float32(1.0), np.zeros(1, dtype=np.uint64))["checked"] is False
