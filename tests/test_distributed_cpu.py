@@ -135,3 +135,48 @@ def test_ranks_share_one_seed(seed):
     if seed is not None:
         assert got[0] == seed
     np.random.RandomState(got[0])   # a valid legacy seed
+
+
+class PipelinedOracleRunner(OracleRunner):
+    """The GPU runner's pipelined interface (submit / flush: results come back one or two jobs late) on top of the oracle."""
+
+    DEPTH = 2
+
+    def __init__(self, *a):
+        super().__init__(*a)
+        self.pending = []
+
+    def submit(self, tag, f, alpha, beta, penalty):
+        self.pending.append((tag, self.run(f, alpha, beta, penalty)))
+        out = []
+        while len(self.pending) >= self.DEPTH:
+            tag0, (tr, te) = self.pending.pop(0)
+            out.append((tag0, tr, te))
+        return out
+
+    def flush(self):
+        out = [(tag, tr, te) for tag, (tr, te) in self.pending]
+        self.pending = []
+        return out
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("presample", [False, True])
+def test_pipelined_runner_fills_the_same_result_slots(presample):
+    """run_grid with a runner whose results arrive late (the GPU runner queues the next DP before it reads the previous
+    job's losses) must file every result under its own job, on the streaming-sampler path and on the presampled one."""
+    from kmerpapa_b200 import CV_tools, iupac
+    from kmerpapa_b200.algorithms import bottum_up_array_penalty_plus_pseudo_CV as cv
+
+    M, U = _data()
+    kmers = iupac.matches(GEN_PAT)
+    pre = None
+    if presample:
+        pre = [CV_tools.sample_fold_counts(kmers, M, U, NF, np.random.RandomState(SEED))]
+    out = []
+    for cls in (OracleRunner, PipelinedOracleRunner):
+        runner = cls(GEN_PAT, M, U)
+        out.append(cv.run_grid(GEN_PAT, kmers, None, M, U, ALPHAS, PENS, NF, 1, SEED, runner=runner, gather_device=None,
+                               presampled=pre))
+        assert runner.calls == NF * len(ALPHAS) * len(PENS)
+    assert out[0].tobytes() == out[1].tobytes()
